@@ -1,0 +1,159 @@
+"""Generates tests/golden/*.npz by executing the UNMODIFIED reference model.py (build container
+only -- needs /root/reference).  Run:  python tools/make_golden.py
+
+Every file holds the inputs' seeds, the reference outputs and a checksum of the synthetic weights
+(tests/common.synth_state_dict) so a drift of the generator is detected instead of silently
+mis-comparing.  The reference ships no golden vectors of its own; these files
+are outputs of the reference itself and are what pins oracle/ and the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_import import (MaskInjector, default_hparams, import_reference_model,  # noqa: E402
+                               injected_dropout)
+from tests.common import GOLDEN_DIR, keep_mask, rand_text, synth_state_dict, weights_checksum  # noqa: E402
+
+torch.set_num_threads(8)
+ref = import_reference_model()
+
+
+def build(sd, training=False):
+    model = ref.Tacotron2(default_hparams())
+    model.load_state_dict(sd)
+    return model.train(training)
+
+
+def ref_batched_inference(model, text, keep, thr, max_steps):
+    """Reference modules driven by a loop that mirrors model.py:435-449 row-wise (the reference's
+    own Decoder.inference raises for B > 1)."""
+    dec = model.decoder
+    B = text.shape[0]
+    masks = [keep[t, l].bool() for t in range(max_steps) for l in range(2)]
+    with torch.no_grad(), injected_dropout(ref, MaskInjector(masks)):
+        emb = model.embedding(text).transpose(1, 2)
+        memory = model.encoder.inference(emb)
+        x = dec.get_go_frame(memory)
+        dec.initialize_decoder_states(memory, mask=None)
+        mels, gates, aligns = [], [], []
+        done = torch.zeros(B, dtype=torch.bool); lengths = torch.zeros(B, dtype=torch.int32)
+        while True:
+            x = dec.prenet(x)
+            mel, gate, aw = dec.decode(x)
+            mels.append(mel); gates.append(gate); aligns.append(aw)
+            fire = (torch.sigmoid(gate.data[:, 0]) > thr) & ~done
+            lengths[fire] = len(mels); done |= fire
+            if bool(done.all()) or len(mels) == max_steps:
+                break
+            x = mel
+        lengths[~done] = len(mels)
+        mel, gate, align = dec.parse_decoder_outputs(mels, gates, aligns)
+        mel_masked = mel.clone()
+        if B > 1:
+            pad = torch.arange(mel.shape[2])[None, :] >= lengths[:, None]
+            mel_masked = mel.masked_fill(pad[:, None, :], 0.0)
+        post = mel_masked + model.postnet(mel_masked)
+        if B > 1:
+            post = post.masked_fill(pad[:, None, :], 0.0)
+    return memory, mel, mel_masked, post, gate, align, lengths
+
+
+def calibrate_gate(sd, text, keep, steps, quantile):
+    """Pick the gate weight sign and bias so rows stop at different, non-trivial steps: the sign
+    makes the gate trend upwards over time, the bias puts the threshold at ``quantile`` of the
+    gate values seen after the first 4 steps."""
+    sd = dict(sd); sd["decoder.gate_layer.linear_layer.bias"] = torch.zeros(1)
+    model = build(sd)
+    _, _, _, _, gate, _, _ = ref_batched_inference(model, text, keep, 2.0, steps)
+    g = gate[:, :, 0]
+    sign = 1.0 if float(g[:, steps // 2:].mean()) > float(g[:, :4].mean()) else -1.0
+    g = g * sign
+    return sign, -float(torch.quantile(g[:, 4:].flatten(), quantile))
+
+
+def save(name, **arrays):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def infer_case(name, B, T_text, max_steps, quantile, wseed, tseed, mseed, wscale=2.0):
+    sd = synth_state_dict(wseed, scale=wscale)
+    text = rand_text(B, T_text, tseed)
+    keep = keep_mask((max_steps, 2, B, 256), 0.5, mseed)
+    best = None
+    for qq in (quantile, quantile - 0.03, quantile + 0.02, quantile - 0.06, quantile + 0.04):
+        sign, bias = calibrate_gate(sd, text, keep, max_steps, qq)
+        sd_q = synth_state_dict(wseed, gate_bias=bias, scale=wscale, gate_sign=sign)
+        r = ref_batched_inference(build(sd_q), text, keep, 0.5, max_steps)
+        lengths, gate = r[6], r[4]
+        live = torch.arange(gate.shape[1])[None, :] < lengths[:, None]     # decisions that matter
+        margin = float((torch.sigmoid(gate[:, :, 0]) - 0.5).abs()[live].min())
+        varied = len(set(lengths.tolist())) > 1 or B == 1
+        score = margin if (varied and int(lengths.min()) > 2) else margin * 1e-3
+        if best is None or score > best[0]:
+            best = (score, sign, bias, sd_q, r, margin)
+    _, sign, bias, sd, (memory, mel, mel_masked, post, gate, align, lengths), margin = best
+    model = build(sd)
+    if B == 1:   # cross-check against the reference's OWN inference() entry point
+        model.decoder.max_decoder_steps = max_steps
+        masks = [keep[t, l].bool() for t in range(max_steps) for l in range(2)]
+        with torch.no_grad(), injected_dropout(ref, MaskInjector(masks)):
+            o = model.inference(text)
+        assert torch.equal(o[0], mel) and torch.equal(o[1], post) and torch.equal(o[3], align)
+        assert torch.equal(o[2], gate)
+    print(name, "lengths", lengths.tolist(), "steps", mel.shape[2], "gate margin", margin)
+    save(name, B=B, T_text=T_text, max_steps=max_steps, wseed=wseed, wscale=wscale, tseed=tseed, mseed=mseed,
+         gate_bias=bias, gate_sign=sign, wsum=weights_checksum(sd), memory=memory, mel=mel, mel_masked=mel_masked,
+         mel_post=post, gate=gate, align=align, mel_lengths=lengths, gate_margin=margin)
+
+
+def forward_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
+    sd = synth_state_dict(wseed, scale=wscale)
+    g = torch.Generator().manual_seed(seed)
+    text = rand_text(B, T_text, seed + 1)
+    tl = torch.sort(torch.randint(T_text // 3, T_text + 1, (B,), generator=g), descending=True)[0]
+    tl[0] = T_text
+    ol = torch.randint(T_mel // 3, T_mel + 1, (B,), generator=g); ol[1] = T_mel
+    mels = torch.randn(B, 80, T_mel, generator=g)
+    pk = keep_mask((T_mel + 1, 2, B, 256), 0.5, seed + 2)
+    ak = keep_mask((T_mel, B, 1024), 0.1, seed + 3)
+    dk = keep_mask((T_mel, B, 1024), 0.1, seed + 4)
+    ek = keep_mask((3, B, 512, T_text), 0.5, seed + 5)
+    qk4 = keep_mask((4, B, 512, T_mel), 0.5, seed + 6)
+    qk1 = keep_mask((B, 80, T_mel), 0.5, seed + 7)
+    model = build(sd, training)
+    if training:
+        masks = [ek[i].bool() for i in range(3)] + [pk[:, 0].bool(), pk[:, 1].bool()]
+        for t in range(T_mel):
+            masks += [ak[t].bool(), dk[t].bool()]
+        masks += [qk4[i].bool() for i in range(4)] + [qk1.bool()]
+    else:
+        masks = [pk[:, 0].bool(), pk[:, 1].bool()]
+    with torch.no_grad(), injected_dropout(ref, MaskInjector(masks)) as inj:
+        emb = model.embedding(text).transpose(1, 2)
+    with torch.no_grad(), injected_dropout(ref, MaskInjector(masks)) as inj:
+        out = model((text, tl, mels, int(tl.max()), ol))
+        assert inj.calls == len(masks)
+    sd_after = model.state_dict()
+    save(name, training=int(training), B=B, T_text=T_text, T_mel=T_mel, wseed=wseed, seed=seed, wscale=wscale,
+         wsum=weights_checksum(sd), text_lengths=tl, output_lengths=ol, mels_in=mels,
+         mel=out[0], mel_post=out[1], gate=out[2], align=out[3],
+         bn0_running_mean=sd_after["encoder.convolutions.0.1.running_mean"],
+         bn0_running_var=sd_after["encoder.convolutions.0.1.running_var"])
+
+
+if __name__ == "__main__":
+    infer_case("infer_b1_t50", 1, 50, 40, 0.95, 1234, 11, 12)
+    infer_case("infer_b4_t24", 4, 24, 32, 0.93, 1234, 21, 22)
+    infer_case("infer_b3_t37", 3, 37, 16, 0.90, 77, 31, 32, wscale=1.0)
+    forward_case("forward_train_b4", True, 4, 24, 12, 1234, 40)
+    forward_case("forward_eval_b4", False, 4, 24, 12, 1234, 50)
