@@ -1,0 +1,190 @@
+/*
+ * t2b200.h -- C ABI of libt2b200.so, the B200 (sm_100a) Tacotron 2 mel-spectrogram engine.
+ *
+ * The reference (NVIDIA/tacotron2) has no FFI / plugin layer: its hot path is ordinary Python
+ * methods on nn.Modules.  This header is therefore the boundary a
+ * maintainer of the reference would bind (ctypes stub in INTEGRATION.md) to replace, one for one,
+ * the bodies of
+ *
+ *     Encoder.inference / Encoder.forward     model.py:173-201     -> t2_encoder_forward
+ *     Decoder.inference                       model.py:418-454     -> t2_decoder_run (mode INFER)
+ *     Decoder.forward  (teacher forcing)      model.py:381-416     -> t2_decoder_run (mode TEACHER)
+ *       Prenet.forward                        model.py:97-100         (inside, per step / hoisted)
+ *       Decoder.decode                        model.py:340-379        (inside, the persistent loop)
+ *       Attention.forward / LocationLayer     model.py:22-26, 43-86   (inside)
+ *       initialize_decoder_states             model.py:258-289        (inside: processed_memory GEMM)
+ *     Postnet.forward (+ residual add)        model.py:141-146, 511, 524  -> t2_postnet_forward
+ *     Tacotron2.inference, host buffers       model.py:517-529     -> t2_infer_host
+ *
+ * Conventions
+ *   - plain C types only; every tensor argument is a raw pointer into DEVICE memory of the current
+ *     CUDA device unless its name ends in _host; all float tensors are fp32, contiguous;
+ *   - the caller owns every buffer; the library allocates only inside T2Model (packed weights) and
+ *     never frees caller memory; scratch comes from the caller-provided workspace (size queries);
+ *   - work is enqueued on the given stream (a cudaStream_t passed as void*); no call synchronises
+ *     the device unless documented (t2_infer_host does, it returns host data);
+ *   - every function returns 0 on success or a negative T2_ERR_* code; t2_last_error() returns a
+ *     thread-local message for the last failure.  Nothing falls back to a CPU path.
+ */
+#ifndef T2B200_H_
+#define T2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2_ABI_VERSION 1
+
+#define T2_OK               0
+#define T2_ERR_INVALID     -1   /* bad argument / unsupported shape                     */
+#define T2_ERR_CUDA        -2   /* a CUDA runtime call failed (message has the detail)  */
+#define T2_ERR_WORKSPACE   -3   /* workspace too small                                  */
+#define T2_ERR_UNSUPPORTED -4   /* hyper-parameters outside what the kernels implement  */
+#define T2_ERR_WATCHDOG    -5   /* a device-side wait timed out (kernel aborted itself)  */
+
+typedef struct T2Model T2Model; /* opaque: configuration + packed device-side weights */
+
+/* Hyper-parameters the model code reads (hparams.py:40-75).  The kernels are specialised for the
+ * reference defaults; t2_model_create returns T2_ERR_UNSUPPORTED for anything else. */
+typedef struct T2Config {
+  int32_t n_mel_channels;              /* 80   */
+  int32_t n_symbols;                   /* 148  */
+  int32_t symbols_embedding_dim;       /* 512  */
+  int32_t encoder_kernel_size;         /* 5    */
+  int32_t encoder_n_convolutions;      /* 3    */
+  int32_t encoder_embedding_dim;       /* 512  */
+  int32_t attention_rnn_dim;           /* 1024 */
+  int32_t decoder_rnn_dim;             /* 1024 */
+  int32_t prenet_dim;                  /* 256  */
+  int32_t attention_dim;               /* 128  */
+  int32_t attention_location_n_filters;    /* 32 */
+  int32_t attention_location_kernel_size;  /* 31 */
+  int32_t postnet_embedding_dim;       /* 512  */
+  int32_t postnet_kernel_size;         /* 5    */
+  int32_t postnet_n_convolutions;      /* 5    */
+  float   p_attention_dropout;         /* 0.1  */
+  float   p_decoder_dropout;           /* 0.1  */
+  float   bn_eps;                      /* 1e-5 */
+} T2Config;
+
+/* Number of entries of the weight table: the reference state_dict in its own order
+ * (84 tensors = 60 parameters + 24 BatchNorm buffers). */
+#define T2_NUM_WEIGHTS 84
+
+/* Decoder implementations selectable at run time (both are CUDA; there is no CPU path). */
+#define T2_IMPL_AUTO        0   /* persistent kernel when the shape allows, else STEPWISE */
+#define T2_IMPL_STEPWISE    1   /* one fp32 kernel sequence per step (bring-up / cross-check) */
+#define T2_IMPL_PERSISTENT  2   /* one persistent cooperative tcgen05 kernel for the whole loop */
+
+#define T2_MODE_INFER    0      /* Decoder.inference: free running, prenet on the fed-back frame */
+#define T2_MODE_TEACHER  1      /* Decoder.forward : teacher forced, exactly n_steps_cap steps  */
+
+int         t2_abi_version(void);
+const char* t2_last_error(void);
+
+/* Fills {sm_count, cc_major, cc_minor, l2_bytes, max_smem_optin} of the current device. */
+int t2_device_info(int32_t out[5]);
+
+/* weights[i]: device pointer to the i-th state_dict tensor (fp32; the three int64
+ * num_batches_tracked entries are ignored and may be NULL).  The model keeps the pointers (not
+ * copies) of the fp32 tensors it streams directly and builds packed copies of the rest, so the
+ * caller must re-create (or t2_model_refresh) the handle after the parameters change. */
+int t2_model_create(T2Model** out, const T2Config* cfg, const void* const* weights,
+                    int32_t n_weights, void* stream);
+int t2_model_refresh(T2Model* m, const void* const* weights, int32_t n_weights, void* stream);
+int t2_model_destroy(T2Model* m);
+
+/* ---- Encoder (model.py:149-201) --------------------------------------------------------------
+ * text (B, T) int64 symbol ids  ->  memory (B, T, 512).
+ * lengths: NULL = Encoder.inference (every row full length); else (B) int32, sorted descending,
+ * lengths[0] == T = Encoder.forward's packed-sequence semantics (zeros at padded positions).
+ * training != 0: batch-statistics BatchNorm (+ running stat update into the caller's tensors)
+ * and dropout(0.5) with keep masks (3, B, 512, T) uint8 or Philox(seed) when NULL. */
+typedef struct T2EncoderArgs {
+  const int64_t* text;                 /* (B, T) symbol ids, or NULL when `embedded` is given        */
+  const float* embedded;               /* (B, T, 512) embedded inputs (model.py:503 before transpose) */
+  const int32_t* lengths; int32_t B, T;
+  int32_t training; const uint8_t* keep; uint64_t seed;
+  float* memory;                       /* out (B, T, 512) */
+  void* ws; size_t ws_bytes;
+} T2EncoderArgs;
+size_t t2_encoder_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
+int    t2_encoder_forward(T2Model* m, const T2EncoderArgs* a, void* stream);
+
+/* ---- Decoder (model.py:204-454) --------------------------------------------------------------
+ * One call runs the whole autoregressive loop.
+ *   memory (B, T_enc, 512); memory_lengths (B) int32 or NULL (no masking, model.py:432).
+ *   INFER  : go frame -> [prenet -> decode -> stop test] x n; per-row stop latch
+ *            done[b] |= sigmoid(gate[b]) > gate_threshold  (predicate of model.py:443);
+ *            the loop ends when every row has fired or after n_steps_cap (= max_decoder_steps);
+ *            rows that fired keep decoding, mel_lengths[b] = first firing step + 1.
+ *   TEACHER: teacher_prenet (n_steps_cap, B, 256) = prenet outputs of go frame + targets
+ *            (model.py:396-399); training != 0 applies dropout(p_att / p_dec) to the recurrent
+ *            hidden states (model.py:355-356, 370-371) with att_keep / dec_keep
+ *            (n_steps_cap, B, 1024) uint8 or Philox when NULL.
+ *   prenet_keep: (n_steps_cap, 2, B, 256) uint8 keep masks for the always-on prenet dropout
+ *            (model.py:99), or NULL => in-kernel Philox4x32-10 keyed by (seed, step).
+ * Outputs (row-major): mel (B, T_cap, 80), gate (B, T_cap), align (B, T_cap, T_enc) where
+ * T_cap = n_steps_cap; entries at t >= *n_steps are left untouched.  mel_lengths (B) int32,
+ * n_steps (1) int32 on the device. */
+typedef struct T2DecoderArgs {
+  int32_t mode, impl, training;
+  const float* memory; const int32_t* memory_lengths; int32_t B, T_enc, n_steps_cap;
+  const float* teacher_prenet;
+  const uint8_t* prenet_keep; const uint8_t* att_keep; const uint8_t* dec_keep;
+  uint64_t seed;
+  float gate_threshold, score_mask_value;
+  float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
+  void* ws; size_t ws_bytes;
+} T2DecoderArgs;
+size_t t2_decoder_workspace_bytes(const T2Model* m, int32_t B, int32_t T_enc, int32_t n_steps_cap);
+int    t2_decoder_run(T2Model* m, const T2DecoderArgs* a, void* stream);
+
+/* Prenet over a block of frames (teacher forcing hoists it out of the loop, model.py:399):
+ * frames (M, 80) -> out (M, 256); keep (2, M, 256) uint8 or NULL => Philox(seed). */
+int t2_prenet_forward(T2Model* m, const float* frames, int32_t M, const uint8_t* keep,
+                      uint64_t seed, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Postnet (model.py:103-146) + residual (model.py:511 / 524) ------------------------------
+ * mel (B, T, 80) time-major per row (the decoder's native storage; the reference's (B,80,T)
+ * tensor is a transposed view of exactly this, model.py:336)  ->  mel_post (B, 80, T) contiguous
+ * = mel^T + postnet(mel^T).  lengths (B) int32 or NULL: frames t >= lengths[b] of the INPUT are
+ * treated as zero and the output there is zero (batched-inference padding, see README). */
+typedef struct T2PostnetArgs {
+  const float* mel;
+  int64_t mel_batch_stride;            /* elements between rows b and b+1 of mel; 0 = T*80 */
+  const int32_t* lengths; int32_t B, T;
+  int32_t training; const uint8_t* keep; uint64_t seed;
+  int32_t add_residual;                /* 1: mel_post = mel^T + postnet(mel^T) (model.py:511, 524); 0: postnet only */
+  float* mel_post;
+  void* ws; size_t ws_bytes;
+} T2PostnetArgs;
+size_t t2_postnet_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
+int    t2_postnet_forward(T2Model* m, const T2PostnetArgs* a, void* stream);
+
+/* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
+ * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
+ * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on
+ * `stream`, copies D2H and synchronises the stream.  ws is device memory of
+ * t2_infer_workspace_bytes(). */
+size_t t2_infer_workspace_bytes(const T2Model* m, int32_t B, int32_t T_text, int32_t max_steps);
+int    t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_text,
+                     int32_t max_steps, float gate_threshold, uint64_t seed, int32_t impl,
+                     float* mel_post_host, int32_t* mel_lengths_host, int32_t* n_steps_host,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- self tests / instrumentation -------------------------------------------------------------
+ * t2_selftest_umma: runs the tcgen05 split-fp16 GEMM engine used by the persistent decoder on a
+ * (64 x K) x (N x K)^T problem and writes C (64 x N) fp32; used by tests/test_umma_gemm.py. */
+int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes,
+                     float* C, void* stream);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+int64_t t2_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2B200_H_ */

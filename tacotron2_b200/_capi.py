@@ -1,0 +1,108 @@
+"""ctypes binding of libt2b200.so (include/t2b200.h).  Importing this module never touches CUDA;
+``lib()`` loads the shared library and raises loudly when it is missing -- there is NO CPU or
+PyTorch fallback for the hot path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt2b200.so")
+
+T2_NUM_WEIGHTS = 84
+IMPL_AUTO, IMPL_STEPWISE, IMPL_PERSISTENT = 0, 1, 2
+MODE_INFER, MODE_TEACHER = 0, 1
+
+EXPORTS = [
+    "t2_abi_version", "t2_last_error", "t2_device_info", "t2_model_create", "t2_model_refresh",
+    "t2_model_destroy", "t2_encoder_workspace_bytes", "t2_encoder_forward",
+    "t2_decoder_workspace_bytes", "t2_decoder_run", "t2_prenet_forward",
+    "t2_postnet_workspace_bytes", "t2_postnet_forward", "t2_infer_workspace_bytes", "t2_infer_host",
+    "t2_selftest_umma", "t2_kernel_launch_count",
+]
+
+
+class T2Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mel_channels", "n_symbols", "symbols_embedding_dim", "encoder_kernel_size",
+        "encoder_n_convolutions", "encoder_embedding_dim", "attention_rnn_dim", "decoder_rnn_dim",
+        "prenet_dim", "attention_dim", "attention_location_n_filters",
+        "attention_location_kernel_size", "postnet_embedding_dim", "postnet_kernel_size",
+        "postnet_n_convolutions")] + [("p_attention_dropout", C.c_float),
+                                      ("p_decoder_dropout", C.c_float), ("bn_eps", C.c_float)]
+
+
+class T2EncoderArgs(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("embedded", C.c_void_p), ("lengths", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32),
+                ("training", C.c_int32), ("keep", C.c_void_p), ("seed", C.c_uint64),
+                ("memory", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+class T2DecoderArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("impl", C.c_int32), ("training", C.c_int32),
+                ("memory", C.c_void_p), ("memory_lengths", C.c_void_p),
+                ("B", C.c_int32), ("T_enc", C.c_int32), ("n_steps_cap", C.c_int32),
+                ("teacher_prenet", C.c_void_p), ("prenet_keep", C.c_void_p),
+                ("att_keep", C.c_void_p), ("dec_keep", C.c_void_p), ("seed", C.c_uint64),
+                ("gate_threshold", C.c_float), ("score_mask_value", C.c_float),
+                ("mel", C.c_void_p), ("gate", C.c_void_p), ("align", C.c_void_p),
+                ("mel_lengths", C.c_void_p), ("n_steps", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+class T2PostnetArgs(C.Structure):
+    _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
+                ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
+                ("seed", C.c_uint64), ("add_residual", C.c_int32), ("mel_post", C.c_void_p), ("ws", C.c_void_p),
+                ("ws_bytes", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises RuntimeError if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            "tacotron2_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C tacotron2_b200/csrc`).  There is no CPU / PyTorch fallback "
+            "for the hot path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.t2_abi_version.restype = C.c_int
+    L.t2_last_error.restype = C.c_char_p
+    L.t2_kernel_launch_count.restype = C.c_int64
+    L.t2_device_info.argtypes = [C.POINTER(C.c_int32)]
+    L.t2_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(T2Config), C.POINTER(C.c_void_p),
+                                  C.c_int32, C.c_void_p]
+    L.t2_model_refresh.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
+    L.t2_model_destroy.argtypes = [C.c_void_p]
+    for n in ("t2_encoder_workspace_bytes", "t2_postnet_workspace_bytes"):
+        getattr(L, n).restype = C.c_size_t
+        getattr(L, n).argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    for n in ("t2_decoder_workspace_bytes", "t2_infer_workspace_bytes"):
+        getattr(L, n).restype = C.c_size_t
+        getattr(L, n).argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    L.t2_encoder_forward.argtypes = [C.c_void_p, C.POINTER(T2EncoderArgs), C.c_void_p]
+    L.t2_decoder_run.argtypes = [C.c_void_p, C.POINTER(T2DecoderArgs), C.c_void_p]
+    L.t2_postnet_forward.argtypes = [C.c_void_p, C.POINTER(T2PostnetArgs), C.c_void_p]
+    L.t2_prenet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.t2_infer_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]
+    L.t2_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]
+    if L.t2_abi_version() != 1:
+        raise RuntimeError("libt2b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+class T2Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise T2Error("libt2b200 error %d: %s" % (rc, lib().t2_last_error().decode()))

@@ -1,0 +1,39 @@
+// Decoder workspace layout shared by the stepwise and the persistent implementation.
+#pragma once
+#include "model.h"
+
+namespace t2 {
+
+constexpr int kMaxBatch = 1024;
+
+struct DecoderCtrl {
+  int all_done;            // every row has fired (INFER) -> remaining work is skipped
+  int error;               // device-side watchdog / consistency error code (0 = ok)
+  int pad_[2];
+  unsigned int bar_count;  // grid barrier of the persistent kernel
+  unsigned int bar_gen;
+  int pad2_[2];
+  int done[kMaxBatch];     // per-row stop latch
+};
+
+struct DecoderWs {
+  float* pm;               // processed_memory (B, T, 128)          model.py:288
+  char* state_begin; size_t state_bytes;   // zero-initialised block (model.py:258-284):
+  float *ah, *ac, *dh, *dc;                // (B, 1024) each
+  float* ctx;              // (B, 512)
+  float *aw, *awc;         // (B, T)
+  float *x1, *x2;          // prenet activations (B, 256)
+  float* gates;            // (B, 4096)
+  float* proj;             // (B, 81)
+  DecoderCtrl* ctrl;
+  char* persistent; size_t persistent_bytes;  // extra region used by the persistent kernel
+};
+
+size_t decoder_ws_bytes(int B, int T, int cap);
+size_t persistent_ws_bytes(int B, int T);
+int decoder_ws_carve(const T2DecoderArgs* a, DecoderWs* w);
+int decoder_run_stepwise(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);
+int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);
+bool persistent_supported(const T2Model* m, const T2DecoderArgs* a);
+
+}  // namespace t2

@@ -1,0 +1,872 @@
+// T2_IMPL_PERSISTENT: the whole autoregressive decoder loop (model.py:381-454) as ONE persistent
+// cooperative sm_100a kernel.
+//
+//   * 128 CTAs (one per SM), 512 threads each.  CTA c owns hidden units [8c, 8c+8) of BOTH LSTM
+//     cells (attention_rnn, decoder_rnn): their cell state lives in registers for the whole loop,
+//     their gate pre-activations accumulate in tensor memory (TMEM) across events.
+//   * "activation driven" schedule: whenever a new activation block (x2, ah, ctx, dh, x1) is
+//     complete, every CTA streams it ONCE through a shared-memory ring (bulk async copies, TMA
+//     engine) together with the slices of every weight matrix that consumes it and issues
+//     tcgen05.mma (M = 64 batch rows, N = 8..32 rows of W, fp32 accumulate in TMEM):
+//        x2_t  -> att gates += W_ih^a[:, :256] x2                          -> ah_t, ac_t
+//        ah_t  -> dec gates += W_ih^d[:, :1024] ah ; att gates(t+1) = W_hh^a ah ; q = W_q ah
+//        ctx_t -> dec gates += W_ih^d[:, 1024:] ctx ; att gates(t+1) += W_ih^a[:, 256:] ctx ;
+//                 proj = W_P[:, 1024:] ctx                                  -> dh_t, dc_t
+//        dh_t  -> proj += W_P[:, :1024] dh ; dec gates(t+1) = W_hh^d dh    -> mel_t, gate_t, x1
+//        x1    -> x2_(t+1) = relu(W_2 x1) * mask
+//     W_P stacks linear_projection, gate_layer and (W_1 . W_proj), so the first prenet layer of the
+//     NEXT step is computed from [dh; ctx] directly (model.py:97-100, 373-378, 449).
+//   * fp32-grade arithmetic on fp16 tensor cores: every operand is split x = hi + lo (two fp16), the
+//     product is hi*hi + lo*hi + hi*lo accumulated in fp32 (3 MMAs) -- DESIGN.md "precision".
+//   * location-sensitive attention (model.py:43-86) runs per batch row on CTA b with warp-shuffle
+//     reductions; previous / cumulative attention weights stay in shared memory across steps.
+//   * events are separated by a grid-wide barrier (global atomic counter + generation flag).
+#include <cooperative_groups.h>
+#include <vector>
+
+#include "decoder.h"
+#include "gemm_f32.cuh"
+#include "umma.cuh"
+
+namespace t2 {
+
+namespace {
+
+constexpr int kG = 128;               // CTAs
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kStages = 4;
+constexpr int kRows = 64;             // MMA M (batch rows, zero padded)
+constexpr int kXChunkBytes = kRows * kChunkK * 2 * 2;   // hi + lo planes = 16 KiB
+constexpr int kWStageMax = 72 * kChunkK * 2 * 2;        // up to 72 W rows per stage = 18 KiB
+constexpr int kStageBytes = kXChunkBytes + kWStageMax;
+constexpr int kTmemCols = 128;
+constexpr int kColA = 0, kColD = 32, kColP = 64, kColQ = 72, kColX2 = 80;
+constexpr int kNumEvents = 5;         // x2, ah, ctx, dh, x1
+constexpr int kPCols = 344;           // 80 mel + 1 gate + 256 x1 + 7 pad
+constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 43;
+constexpr unsigned long long kWatchdogCycles = 1ull << 32;   // ~2 s
+
+struct EventPlan {
+  uint32_t w_off;       // byte offset of this CTA's first chunk in the W image buffer
+  uint32_t w_bytes;     // W bytes per chunk (sum over consumers of n*256)
+  int32_t ncons;
+  int32_t n[3];         // rows of W (MMA N) per consumer
+  int32_t col[3];       // TMEM accumulator column per consumer
+};
+struct CtaPlan {
+  EventPlan ev[kNumEvents];
+};
+
+struct PersistentPack {
+  uint8_t* wimg = nullptr; size_t wimg_bytes = 0;
+  CtaPlan* plans = nullptr;           // device, kG entries
+  float* wp_all = nullptr;            // (344, 1536) fp32: proj | gate | W1.Wproj | zero pad
+  float* bias_p = nullptr;            // (344): proj bias | gate bias | W1.b_proj | 0
+  float* bias_a = nullptr;            // (kG, 32) att LSTM bias in TMEM column order
+  float* bias_d = nullptr;            // (kG, 32)
+  int32_t* rows = nullptr;            // scratch row tables for packing
+};
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels (model create time)
+// ---------------------------------------------------------------------------------------------
+// W1P = W1 (256x80) . Wproj (80x1536), b1p = W1 . bproj           (fusing model.py:375-376 into :98)
+__global__ void fuse_prenet_proj_kernel(const float* __restrict__ w1, const float* __restrict__ wp,
+                                        const float* __restrict__ bp, float* __restrict__ out_w,
+                                        float* __restrict__ out_b) {
+  const int r = blockIdx.x;                  // 0..255
+  for (int c = threadIdx.x; c < kDRnn + kEnc; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < kMel; ++k) s = fmaf(w1[r * kMel + k], wp[(long)k * (kDRnn + kEnc) + c], s);
+    out_w[(long)r * (kDRnn + kEnc) + c] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < kMel; ++k) s = fmaf(w1[r * kMel + k], bp[k], s);
+    out_b[r] = s;
+  }
+}
+
+// one consumer of one event: for CTA blockIdx.y, chunk blockIdx.x: write [hi plane | lo plane] of the
+// n rows rows_tab[cta*32 + i] (-1 = zero row) x 64 columns starting at kcol0 + chunk*64.
+__global__ void pack_consumer_kernel(const float* __restrict__ src, int ld, int kcol0,
+                                     const int32_t* __restrict__ rows_tab, const CtaPlan* __restrict__ plans,
+                                     int ev, int cons, uint8_t* __restrict__ wimg) {
+  const int cta = blockIdx.y, chunk = blockIdx.x;
+  const EventPlan& ep = plans[cta].ev[ev];
+  if (cons >= ep.ncons) return;
+  const int n = ep.n[cons];
+  uint32_t off = ep.w_off + (uint32_t)chunk * ep.w_bytes;
+  for (int i = 0; i < cons; ++i) off += ep.n[i] * 256;
+  __half* hi = reinterpret_cast<__half*>(wimg + off);
+  __half* lo = hi + n * 64;
+  for (int i = threadIdx.x; i < n * 64; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    const int srow = rows_tab[cta * 32 + r];
+    const float v = srow >= 0 ? src[(long)srow * ld + kcol0 + chunk * 64 + k] : 0.f;
+    __half h, l;
+    split_fp16(v, h, l);
+    const uint32_t e = img_elem_offset(r, k);
+    hi[e] = h; lo[e] = l;
+  }
+}
+
+__global__ void pack_lstm_bias_kernel(const float* __restrict__ b_sum, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // cta*32 + col
+  if (i >= kG * 32) return;
+  const int cta = i >> 5, col = i & 31, ul = col >> 2, g = col & 3;
+  out[i] = b_sum[g * 1024 + cta * 8 + ul];
+}
+
+// fp32 rows (n_rows x K, ld) -> operand images (chunks x [hi|lo] planes of 64 x 64), rows >= n_rows zero
+__global__ void rows_to_image_kernel(const float* __restrict__ src, long ld, int n_rows, int K,
+                                     long src_block_stride, uint8_t* __restrict__ dst, long dst_block_stride) {
+  const float* s = src + (long)blockIdx.y * src_block_stride;
+  uint8_t* d = dst + (long)blockIdx.y * dst_block_stride;
+  const int chunk = blockIdx.x;
+  __half* hi = reinterpret_cast<__half*>(d + (long)chunk * kXChunkBytes);
+  __half* lo = hi + kRows * kChunkK;
+  for (int i = threadIdx.x; i < kRows * kChunkK; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    const int kk = chunk * kChunkK + k;
+    const float v = (r < n_rows && kk < K) ? s[(long)r * ld + kk] : 0.f;
+    __half h, l;
+    split_fp16(v, h, l);
+    const uint32_t e = img_elem_offset(r, k);
+    hi[e] = h; lo[e] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void watchdog_trap(DecoderCtrl* ctrl, int code) {
+  if (ctrl) ctrl->error = code;
+  __threadfence_system();
+  __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DecoderCtrl* ctrl, int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, code);
+  }
+}
+
+// grid-wide barrier: counter + generation (release / acquire at gpu scope).  Also orders the generic
+// proxy stores of the epilogues before the async-proxy (bulk copy) reads of the next event.
+__device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& gen) {
+  ptx::fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ctrl->bar_count, 1u);
+    if (prev == gridDim.x - 1) {
+      ctrl->bar_count = 0;
+      __threadfence();
+      atomicExch(&ctrl->bar_gen, gen + 1);
+    } else {
+      const unsigned long long t0 = clock64();
+      while (true) {
+        unsigned int g;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(&ctrl->bar_gen) : "memory");
+        if (g != gen) break;
+        if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 100);
+      }
+    }
+    __threadfence();
+  }
+  gen += 1;
+  __syncthreads();
+  ptx::fence_proxy_async();
+}
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct Ring {
+  uint8_t* stage0;    // kStages buffers of kStageBytes each
+  __device__ __forceinline__ uint8_t* stage(uint32_t s) const { return stage0 + s * kStageBytes; }
+  uint64_t* full;     // [kStages]
+  uint64_t* empty;    // [kStages]
+  uint64_t* acc;      // accumulator-ready barrier
+  uint32_t p_stage, p_phase;   // producer cursor (thread 0 of warp 0)
+  uint32_t c_stage, c_phase;   // consumer cursor (thread 0 of warp 1)
+  uint32_t acc_phase;          // all threads
+};
+
+// Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight slices through the
+// ring and issues the MMAs.  Called by all threads; returns after the accumulators are complete.
+__device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
+                                          const uint8_t* w_img, int chunks, uint32_t fresh_mask,
+                                          int passes, uint32_t tmem_base, DecoderCtrl* ctrl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (ep.ncons == 0) return;           // this CTA has no consumer of this activation
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < chunks; ++i) {
+        mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
+        uint8_t* st = rg.stage(rg.p_stage);
+        ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
+        ptx::bulk_g2s(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage]);
+        ptx::bulk_g2s(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
+                      &rg.full[rg.p_stage]);
+        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < chunks; ++i) {
+        mbar_wait(&rg.full[rg.c_stage], rg.c_phase, ctrl, 201);
+        ptx::tc_fence_after();
+        const uint32_t xs = ptx::smem_u32(rg.stage(rg.c_stage));
+        uint32_t ws = xs + kXChunkBytes;
+        for (int c = 0; c < ep.ncons; ++c) {
+          const uint32_t n = (uint32_t)ep.n[c];
+          const uint32_t idesc = ptx::make_idesc_f16_m64(n);
+          const uint32_t d = tmem_base + (uint32_t)ep.col[c];
+          const bool fresh = (fresh_mask >> c) & 1u;
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            const uint64_t a_hi = ptx::make_smem_desc(xs + kk * 256, 128, 1024);
+            const uint64_t a_lo = ptx::make_smem_desc(xs + kRows * kChunkK * 2 + kk * 256, 128, 1024);
+            const uint64_t b_hi = ptx::make_smem_desc(ws + kk * 256, 128, 1024);
+            const uint64_t b_lo = ptx::make_smem_desc(ws + n * kChunkK * 2 + kk * 256, 128, 1024);
+            const uint32_t acc0 = (fresh && i == 0 && kk == 0) ? 0u : 1u;
+            ptx::umma_f16(d, a_hi, b_hi, idesc, acc0);
+            if (passes == 3) {
+              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          ws += n * kChunkK * 2 * 2;
+        }
+        ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
+        if (++rg.c_stage == kStages) { rg.c_stage = 0; rg.c_phase ^= 1; }
+      }
+      ptx::umma_commit(rg.acc);
+    }
+    __syncwarp();
+  }
+  mbar_wait(rg.acc, rg.acc_phase, ctrl, 202);
+  rg.acc_phase ^= 1;
+  ptx::tc_fence_after();
+}
+
+struct KParams {
+  const PersistentPack* pk_unused;
+  const CtaPlan* plans;
+  const uint8_t* wimg;
+  const float* bias_a; const float* bias_d; const float* bias_p;
+  // attention weights (fp32, caller's tensors)
+  const float* w_loc; const float* w_ld; const float* w_v;
+  // tensors
+  const float* memory; const float* pm; const int32_t* mem_len;
+  const uint8_t* prenet_keep; const uint8_t* att_keep; const uint8_t* dec_keep;
+  // activation images (workspace)
+  uint8_t* x2_img; uint8_t* ah_img; uint8_t* ctx_img; uint8_t* dh_img; uint8_t* x1_img;
+  const uint8_t* teacher_x2_img;   // (cap, 4 chunks) or null
+  float* q;                         // (64, 128) fp32
+  float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
+  DecoderCtrl* ctrl;
+  int B, T, cap, infer, training, passes;
+  float gate_threshold, score_mask_value, p_att, p_dec;
+  uint64_t seed;
+};
+
+__device__ __forceinline__ void store_split2(uint8_t* img, int row, int k, float v0, float v1) {
+  // two adjacent K elements (k even) of an activation image: 4-byte stores into the hi and lo planes
+  const int chunk = k >> 6, kc = k & 63;
+  __half2 h, l;
+  __half h0, l0, h1, l1;
+  split_fp16(v0, h0, l0);
+  split_fp16(v1, h1, l1);
+  h = __halves2half2(h0, h1); l = __halves2half2(l0, l1);
+  __half* hi = reinterpret_cast<__half*>(img + (size_t)chunk * kXChunkBytes);
+  __half* lo = hi + kRows * kChunkK;
+  const uint32_t e = img_elem_offset(row, kc);
+  *reinterpret_cast<__half2*>(hi + e) = h;
+  *reinterpret_cast<__half2*>(lo + e) = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const KParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int T = p.T, TP = T + kLocK - 1;
+
+  // ---- shared memory carve-up ----
+  uint8_t* sp = smem_raw;
+  Ring rg;
+  rg.stage0 = sp; sp += kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
+  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
+  int* s_live = reinterpret_cast<int*>(sp); sp += 16;
+  float* s_bias_a = reinterpret_cast<float*>(sp); sp += 32 * 4;
+  float* s_bias_d = reinterpret_cast<float*>(sp); sp += 32 * 4;
+  float* s_wld_t = reinterpret_cast<float*>(sp); sp += kLocF * kAtt * 4;      // [c][d]
+  float* s_wloc = reinterpret_cast<float*>(sp); sp += kLocF * 2 * kLocK * 4;
+  float* s_v = reinterpret_cast<float*>(sp); sp += kAtt * 4;
+  float* s_q = reinterpret_cast<float*>(sp); sp += kAtt * 4;
+  float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
+  float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
+  float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
+  float* s_e = reinterpret_cast<float*>(sp); sp += ((T + 3) & ~3) * 4;
+  float* s_loc = reinterpret_cast<float*>(sp);                                // [32][T]
+
+  rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
+    ptx::mbar_init(rg.acc, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  for (int i = tid; i < 32; i += kThreads) { s_bias_a[i] = p.bias_a[cta * 32 + i]; s_bias_d[i] = p.bias_d[cta * 32 + i]; }
+  for (int i = tid; i < kLocF * kAtt; i += kThreads) {
+    const int d = i / kLocF, c = i - d * kLocF;
+    s_wld_t[c * kAtt + d] = p.w_ld[i];
+  }
+  for (int i = tid; i < kLocF * 2 * kLocK; i += kThreads) s_wloc[i] = p.w_loc[i];
+  for (int i = tid; i < kAtt; i += kThreads) s_v[i] = p.w_v[i];
+  for (int i = tid; i < TP; i += kThreads) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }   // model.py:274-277
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const CtaPlan& plan = p.plans[cta];
+  DecoderCtrl* ctrl = p.ctrl;
+  unsigned int bar_gen = 0;
+  // epilogue role of this thread: TMEM lane quadrant q = warp % 4 (hardware rule), column group
+  // cg = warp / 4; valid rows are lanes 0..15 of each quadrant for M = 64 accumulators.
+  const int quad = warp & 3, cg = warp >> 2;
+  const int row = quad * 16 + lane;                   // batch row of this thread (lane < 16)
+  const bool erow = lane < 16 && row < p.B;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  float c_att[2] = {0.f, 0.f}, c_dec[2] = {0.f, 0.f};  // cell states of units 8*cta + 2*cg + {0,1}
+  const bool has_q = cta >= kQCta0 && cta < kQCta0 + kQCtas;
+  const bool has_x2 = cta >= kX2Cta0 && cta < kX2Cta0 + kX2Ctas;
+  const bool has_p = cta >= kPCta0 && cta < kPCta0 + kPCtas;
+  const int halfk = (kLocK - 1) / 2;
+  int t = 0;
+  for (; t < p.cap; ++t) {
+    // ======== E0: x2_t -> attention LSTM gates, epilogue -> ah_t ==================== model.py:352-356
+    {
+      const uint8_t* x2 = p.infer ? p.x2_img : p.teacher_x2_img + (size_t)t * 4 * kXChunkBytes;
+      run_event(rg, plan.ev[0], x2, p.wimg, 4, t == 0 ? 1u : 0u, p.passes, tmem_base, ctrl);
+      float g[8];
+      ptx::tmem_ld8(t_lane + kColA + cg * 8, g);
+      if (erow) {
+        float hv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float* b = s_bias_a + (cg * 2 + u) * 4;
+          const float gi = sigmoid_fast(g[u * 4 + 0] + b[0]);
+          const float gf = sigmoid_fast(g[u * 4 + 1] + b[1]);
+          const float gg = tanh_fast(g[u * 4 + 2] + b[2]);
+          const float go = sigmoid_fast(g[u * 4 + 3] + b[3]);
+          c_att[u] = gf * c_att[u] + gi * gg;
+          float h = go * tanh_fast(c_att[u]);
+          if (p.training) {
+            const int unit = cta * 8 + cg * 2 + u;
+            const long idx = (long)row * kARnn + unit;
+            const bool keep = p.att_keep ? p.att_keep[(long)t * p.B * kARnn + idx] != 0
+                                         : philox_keep(p.seed, t * 4 + 2, idx, p.p_att);
+            h = keep ? h * (1.f / (1.f - p.p_att)) : 0.f;
+          }
+          hv[u] = h;
+        }
+        store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
+      }
+      ptx::tc_fence_before();
+      grid_barrier(ctrl, bar_gen);                                             // B1: ah_t complete
+    }
+    // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
+    {
+      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, (t == 0 ? 1u : 0u) | 2u | 4u, p.passes, tmem_base, ctrl);
+      if (has_q && cg == 0) {
+        float g[8];
+        ptx::tmem_ld8(t_lane + kColQ, g);
+        if (erow) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p.q[row * kAtt + (cta - kQCta0) * 8 + j] = g[j];
+        }
+      }
+      ptx::tc_fence_before();
+      grid_barrier(ctrl, bar_gen);                                             // B2: q complete
+    }
+    // ======== attention for batch row `cta` ================================== model.py:43-86, 358-365
+    if (cta < p.B) {
+      const int b = cta;
+      for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
+      __syncthreads();
+      for (int i = tid; i < kLocF * T; i += kThreads) {        // location conv          model.py:23
+        const int c = i / T, j = i - c * T;
+        const float* w0 = s_wloc + c * 2 * kLocK;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kLocK; ++k) s = fmaf(w0[k], s_pad0[j + k], s);
+#pragma unroll
+        for (int k = 0; k < kLocK; ++k) s = fmaf(w0[kLocK + k], s_pad1[j + k], s);
+        s_loc[i] = s;
+      }
+      __syncthreads();
+      const int len = p.mem_len ? p.mem_len[b] : T;
+      for (int j = warp; j < T; j += kWarps) {                 // energies               model.py:58-60
+        float part = 0.f;
+#pragma unroll
+        for (int r = 0; r < kAtt / 32; ++r) {
+          const int d = lane + 32 * r;
+          float pa = 0.f;
+#pragma unroll
+          for (int c = 0; c < kLocF; ++c) pa = fmaf(s_wld_t[c * kAtt + d], s_loc[c * T + j], pa);
+          const float x = s_q[d] + pa + p.pm[((long)b * T + j) * kAtt + d];
+          part = fmaf(s_v[d], tanhf(x), part);
+        }
+        part = warp_sum_f(part);
+        if (lane == 0) s_e[j] = (j < len) ? part : p.score_mask_value;       // model.py:79-80
+      }
+      __syncthreads();
+      float mx = -INFINITY;                                     // softmax                model.py:82
+      for (int j = tid; j < T; j += kThreads) mx = fmaxf(mx, s_e[j]);
+      mx = warp_max_f(mx);
+      if (lane == 0) s_red[warp] = mx;
+      __syncthreads();
+      mx = s_red[0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) mx = fmaxf(mx, s_red[w]);
+      __syncthreads();
+      float sum = 0.f;
+      for (int j = tid; j < T; j += kThreads) { const float e = expf(s_e[j] - mx); s_e[j] = e; sum += e; }
+      sum = warp_sum_f(sum);
+      if (lane == 0) s_red[warp] = sum;
+      __syncthreads();
+      sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sum += s_red[w];
+      const float inv = 1.f / sum;
+      for (int j = tid; j < T; j += kThreads) {
+        const float a = s_e[j] * inv;
+        s_e[j] = a;
+        s_pad0[halfk + j] = a;                                                // becomes "previous"
+        s_pad1[halfk + j] += a;                                               // model.py:365
+        p.align[((long)b * p.cap + t) * T + j] = a;
+      }
+      __syncthreads();
+      {                                                           // context                model.py:83-84
+        const int col = tid;                                      // kThreads == kEnc
+        const float* mp = p.memory + (long)b * T * kEnc + col;
+        float s0 = 0.f, s1 = 0.f;
+        int j = 0;
+        for (; j + 1 < T; j += 2) {
+          s0 = fmaf(s_e[j], mp[(long)j * kEnc], s0);
+          s1 = fmaf(s_e[j + 1], mp[(long)(j + 1) * kEnc], s1);
+        }
+        if (j < T) s0 = fmaf(s_e[j], mp[(long)j * kEnc], s0);
+        const float cv = s0 + s1;
+        const float nb = __shfl_down_sync(0xffffffffu, cv, 1);
+        if ((lane & 1) == 0) store_split2(p.ctx_img, b, col, cv, nb);
+      }
+    }
+    grid_barrier(ctrl, bar_gen);                                               // B3: ctx_t complete
+    // ======== E2: ctx_t -> dec gates (rest), next att gates, projection (part); epilogue -> dh_t
+    {
+      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, 4u, p.passes, tmem_base, ctrl);
+      float g[8];
+      ptx::tmem_ld8(t_lane + kColD + cg * 8, g);
+      if (erow) {
+        float hv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float* b = s_bias_d + (cg * 2 + u) * 4;
+          const float gi = sigmoid_fast(g[u * 4 + 0] + b[0]);
+          const float gf = sigmoid_fast(g[u * 4 + 1] + b[1]);
+          const float gg = tanh_fast(g[u * 4 + 2] + b[2]);
+          const float go = sigmoid_fast(g[u * 4 + 3] + b[3]);
+          c_dec[u] = gf * c_dec[u] + gi * gg;
+          float h = go * tanh_fast(c_dec[u]);
+          if (p.training) {
+            const int unit = cta * 8 + cg * 2 + u;
+            const long idx = (long)row * kDRnn + unit;
+            const bool keep = p.dec_keep ? p.dec_keep[(long)t * p.B * kDRnn + idx] != 0
+                                         : philox_keep(p.seed, t * 4 + 3, idx, p.p_dec);
+            h = keep ? h * (1.f / (1.f - p.p_dec)) : 0.f;
+          }
+          hv[u] = h;
+        }
+        store_split2(p.dh_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
+      }
+      ptx::tc_fence_before();
+      grid_barrier(ctrl, bar_gen);                                             // B4: dh_t complete
+    }
+    // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
+    {
+      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, 1u, p.passes, tmem_base, ctrl);
+      if (tid == 0) *s_live = 0;
+      __syncthreads();
+      if (has_p && cg == 0) {
+        float g[8];
+        ptx::tmem_ld8(t_lane + kColP, g);
+        if (erow) {
+          const int pc0 = (cta - kPCta0) * 8;
+          float x1v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pc = pc0 + j;
+            const float v = g[j] + p.bias_p[pc];
+            x1v[j] = 0.f;
+            if (pc < kMel) {
+              p.mel[((long)row * p.cap + t) * kMel + pc] = v;                  // model.py:375-376
+            } else if (pc == kMel) {
+              p.gate[(long)row * p.cap + t] = v;                               // model.py:378
+              if (p.infer) {
+                int done = ctrl->done[row];
+                if (!done && sigmoid_exact(v) > p.gate_threshold) {           // model.py:443
+                  done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
+                }
+                if (!done) atomicAdd(s_live, 1);
+              }
+            } else if (pc < kMel + 1 + kPre) {                                 // first prenet layer of step t+1
+              const int col = pc - (kMel + 1);
+              float r = fmaxf(v, 0.f);
+              if (p.infer && t + 1 < p.cap) {
+                const long idx = (long)row * kPre + col;
+                const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
+                                                : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
+                r = keep ? r * 2.f : 0.f;
+              }
+              x1v[j] = r;
+            }
+          }
+          if (p.infer) {
+            // columns pc0..pc0+7 that are x1 columns: col = pc - 81; pairs may straddle the mel/gate
+            // boundary only in CTA 10 (pc0 = 80): handle element-wise there.
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int pc = pc0 + j;
+              if (pc > kMel && pc < kMel + 1 + kPre) {
+                const int col = pc - (kMel + 1);
+                __half h, l;
+                split_fp16(x1v[j], h, l);
+                __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
+                __half* lo = hi + kRows * kChunkK;
+                const uint32_t e = img_elem_offset(row, col & 63);
+                hi[e] = h; lo[e] = l;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel && tid == 0) {   // the gate CTA
+        *p.n_steps = t + 1;
+        if (p.infer && *s_live == 0) ctrl->all_done = 1;
+        __threadfence();
+      }
+      ptx::tc_fence_before();
+      if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
+      grid_barrier(ctrl, bar_gen);                                             // B5: x1 / stop flag complete
+      int all_done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
+      if (all_done || t + 1 == p.cap) { ++t; break; }
+    }
+    // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
+    {
+      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, 1u, p.passes, tmem_base, ctrl);
+      if (has_x2 && cg == 0) {
+        float g[8];
+        ptx::tmem_ld8(t_lane + kColX2, g);
+        if (erow) {
+          const int col0 = (cta - kX2Cta0) * 8;
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long idx = (long)row * kPre + col0 + j;
+            const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 1) * p.B * kPre + idx] != 0
+                                            : philox_keep(p.seed, (t + 1) * 4 + 1, idx, 0.5f);
+            r[j] = keep ? fmaxf(g[j], 0.f) * 2.f : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) store_split2(p.x2_img, row, col0 + j, r[j], r[j + 1]);
+        }
+      }
+      ptx::tc_fence_before();
+      grid_barrier(ctrl, bar_gen);                                             // B6: x2_(t+1) complete
+    }
+  }
+  // rows that never fired: length = number of steps run (model.py:445-447)
+  if (cta == 0) {
+    __syncthreads();
+    const int ns = p.infer ? t : p.cap;
+    for (int b = tid; b < p.B; b += kThreads)
+      if (!p.infer || !__ldcg(&ctrl->done[b])) p.mel_lengths[b] = ns;
+    if (tid == 0) *p.n_steps = ns;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static size_t persistent_smem_bytes(int T) {
+  const int TP = T + kLocK - 1;
+  size_t n = (size_t)kStages * kStageBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + (size_t)kLocF * kAtt * 4 +
+             kLocF * 2 * kLocK * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 +
+             (size_t)((T + 3) & ~3) * 4 + (size_t)kLocF * T * 4;
+  return n + 1024;
+}
+
+size_t persistent_ws_bytes(int B, int T) {
+  (void)B; (void)T;
+  // activation images: x2 (4 chunks), ah (16), ctx (8), dh (16), x1 (4)  + q (64 x 128 fp32)
+  return (size_t)(4 + 16 + 8 + 16 + 4) * kXChunkBytes + (size_t)kRows * kAtt * 4 + 1024;
+}
+
+bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
+  if (!m->pk) return false;
+  if (m->sm_count < kG) return false;
+  if (a->B > kRows) return false;
+  if (a->mode != T2_MODE_INFER) return false;   // teacher forcing runs on the stepwise path for now
+  if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
+  return true;
+}
+
+int persistent_pack_create(T2Model* m, cudaStream_t s) {
+  PersistentPack* pk = (PersistentPack*)m->pk;
+  if (!pk) { pk = new PersistentPack(); m->pk = pk; }
+  const int kdc = kDRnn + kEnc;
+  // ---- per-CTA plans (host) ----
+  std::vector<CtaPlan> plans(kG);
+  size_t off = 0;
+  for (int c = 0; c < kG; ++c) {
+    const bool hq = c >= kQCta0 && c < kQCta0 + kQCtas, hx = c >= kX2Cta0 && c < kX2Cta0 + kX2Ctas,
+               hp = c >= kPCta0 && c < kPCta0 + kPCtas;
+    CtaPlan& pl = plans[c];
+    memset(&pl, 0, sizeof(pl));
+    auto set = [&](int ev, int chunks, std::initializer_list<std::pair<int, int>> cons) {
+      EventPlan& e = pl.ev[ev];
+      e.ncons = 0; e.w_bytes = 0;
+      for (auto& pr : cons) { e.n[e.ncons] = pr.first; e.col[e.ncons] = pr.second; e.w_bytes += pr.first * 256; e.ncons++; }
+      e.w_off = (uint32_t)off;
+      off += (size_t)chunks * e.w_bytes;
+    };
+    set(0, 4, {{32, kColA}});
+    if (hq) set(1, 16, {{32, kColD}, {32, kColA}, {8, kColQ}}); else set(1, 16, {{32, kColD}, {32, kColA}});
+    if (hp) set(2, 8, {{32, kColD}, {32, kColA}, {8, kColP}}); else set(2, 8, {{32, kColD}, {32, kColA}});
+    if (hp) set(3, 16, {{32, kColD}, {8, kColP}}); else set(3, 16, {{32, kColD}});
+    if (hx) set(4, 4, {{8, kColX2}}); else { pl.ev[4].ncons = 0; pl.ev[4].w_bytes = 0; pl.ev[4].w_off = (uint32_t)off; }
+  }
+  if (off >= (size_t)4 << 30) return fail(T2_ERR_INVALID, "W image too large");
+  if (!pk->wimg) {
+    pk->wimg_bytes = off + 1024;
+    T2_CUDA(cudaMalloc((void**)&pk->wimg, pk->wimg_bytes));
+    T2_CUDA(cudaMalloc((void**)&pk->plans, sizeof(CtaPlan) * kG));
+    T2_CUDA(cudaMalloc((void**)&pk->wp_all, (size_t)kPCols * kdc * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->bias_p, (size_t)kPCols * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->bias_a, (size_t)kG * 32 * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->bias_d, (size_t)kG * 32 * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->rows, (size_t)4 * kG * 32 * 4));
+  }
+  T2_CUDA(cudaMemcpyAsync(pk->plans, plans.data(), sizeof(CtaPlan) * kG, cudaMemcpyHostToDevice, s));
+  T2_CUDA(cudaStreamSynchronize(s));   // `plans` is a host temporary
+  // ---- W_P = [proj (80) ; gate (1) ; W1.Wproj (256) ; 0 (7)] and its bias ----
+  T2_CUDA(cudaMemsetAsync(pk->wp_all, 0, (size_t)kPCols * kdc * 4, s));
+  T2_CUDA(cudaMemsetAsync(pk->bias_p, 0, (size_t)kPCols * 4, s));
+  T2_CUDA(cudaMemcpyAsync(pk->wp_all, m->projgate_w, (size_t)(kMel + 1) * kdc * 4, cudaMemcpyDeviceToDevice, s));
+  T2_CUDA(cudaMemcpyAsync(pk->bias_p, m->projgate_b, (size_t)(kMel + 1) * 4, cudaMemcpyDeviceToDevice, s));
+  fuse_prenet_proj_kernel<<<kPre, 256, 0, s>>>(m->w[W_PRENET0], m->w[W_PROJ_W], m->w[W_PROJ_B],
+                                               pk->wp_all + (size_t)(kMel + 1) * kdc, pk->bias_p + kMel + 1);
+  T2_LAUNCH_CHECK();
+  pack_lstm_bias_kernel<<<(kG * 32 + 255) / 256, 256, 0, s>>>(m->arnn_b, pk->bias_a);
+  T2_LAUNCH_CHECK();
+  pack_lstm_bias_kernel<<<(kG * 32 + 255) / 256, 256, 0, s>>>(m->drnn_b, pk->bias_d);
+  T2_LAUNCH_CHECK();
+  // ---- row tables: [0] LSTM gate rows, [1] q rows, [2] P rows, [3] x2 rows ----
+  std::vector<int32_t> rows((size_t)4 * kG * 32, -1);
+  for (int c = 0; c < kG; ++c) {
+    for (int col = 0; col < 32; ++col) rows[(0 * kG + c) * 32 + col] = (col & 3) * 1024 + c * 8 + (col >> 2);
+    if (c >= kQCta0 && c < kQCta0 + kQCtas) for (int j = 0; j < 8; ++j) rows[(1 * kG + c) * 32 + j] = (c - kQCta0) * 8 + j;
+    if (c >= kPCta0 && c < kPCta0 + kPCtas) for (int j = 0; j < 8; ++j) rows[(2 * kG + c) * 32 + j] = (c - kPCta0) * 8 + j;
+    if (c >= kX2Cta0 && c < kX2Cta0 + kX2Ctas) for (int j = 0; j < 8; ++j) rows[(3 * kG + c) * 32 + j] = (c - kX2Cta0) * 8 + j;
+  }
+  T2_CUDA(cudaMemcpyAsync(pk->rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, s));
+  T2_CUDA(cudaStreamSynchronize(s));
+  const int32_t* r_lstm = pk->rows; const int32_t* r_q = pk->rows + kG * 32;
+  const int32_t* r_p = pk->rows + 2 * kG * 32; const int32_t* r_x2 = pk->rows + 3 * kG * 32;
+  auto pack = [&](const float* src, int ld, int kcol0, int chunks, const int32_t* rt, int ev, int cons) -> int {
+    pack_consumer_kernel<<<dim3(chunks, kG), 256, 0, s>>>(src, ld, kcol0, rt, pk->plans, ev, cons, pk->wimg);
+    T2_LAUNCH_CHECK();
+    return T2_OK;
+  };
+  T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, 0, 4, r_lstm, 0, 0));            // E0: att <- x2
+  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, 0, 16, r_lstm, 1, 0));                   // E1: dec <- ah
+  T2_TRY(pack(m->w[W_ARNN_WHH], kARnn, 0, 16, r_lstm, 1, 1));                 //     att' <- ah
+  T2_TRY(pack(m->w[W_ATT_QUERY], kARnn, 0, 16, r_q, 1, 2));                   //     q <- ah
+  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, kARnn, 8, r_lstm, 2, 0));                // E2: dec <- ctx
+  T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, kPre, 8, r_lstm, 2, 1));         //     att' <- ctx
+  T2_TRY(pack(pk->wp_all, kdc, kDRnn, 8, r_p, 2, 2));                         //     P <- ctx
+  T2_TRY(pack(m->w[W_DRNN_WHH], kDRnn, 0, 16, r_lstm, 3, 0));                 // E3: dec' <- dh
+  T2_TRY(pack(pk->wp_all, kdc, 0, 16, r_p, 3, 1));                            //     P <- dh
+  T2_TRY(pack(m->w[W_PRENET1], kPre, 0, 4, r_x2, 4, 0));                      // E4: x2 <- x1
+  return T2_OK;
+}
+
+void persistent_pack_destroy(T2Model* m) {
+  PersistentPack* pk = (PersistentPack*)m->pk;
+  if (!pk) return;
+  cudaFree(pk->wimg); cudaFree(pk->plans); cudaFree(pk->wp_all); cudaFree(pk->bias_p);
+  cudaFree(pk->bias_a); cudaFree(pk->bias_d); cudaFree(pk->rows);
+  delete pk;
+  m->pk = nullptr;
+}
+
+int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
+  PersistentPack* pk = (PersistentPack*)m->pk;
+  const int B = a->B, T = a->T_enc, cap = a->n_steps_cap;
+  DecoderWs w;
+  T2_TRY(decoder_ws_carve(a, &w));
+  T2_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(DecoderCtrl), s));
+  T2_CUDA(cudaMemsetAsync(w.persistent, 0, w.persistent_bytes, s));          // zero images (model.py:258-284)
+  {  // processed_memory = memory_layer(memory)                                  (model.py:288)
+    GemmArgs g;
+    g.seg[0] = {a->memory, kEnc, m->w[W_ATT_MEMORY], kEnc, kEnc};
+    g.M = B * T; g.N = kAtt; g.C = w.pm; g.ldc = kAtt;
+    T2_TRY(gemm_f32(g, s));
+  }
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  uint8_t* img = (uint8_t*)w.persistent;
+  p.x2_img = img; img += 4 * kXChunkBytes;
+  p.ah_img = img; img += 16 * kXChunkBytes;
+  p.ctx_img = img; img += 8 * kXChunkBytes;
+  p.dh_img = img; img += 16 * kXChunkBytes;
+  p.x1_img = img; img += 4 * kXChunkBytes;
+  p.q = (float*)img;
+  p.plans = pk->plans; p.wimg = pk->wimg; p.bias_a = pk->bias_a; p.bias_d = pk->bias_d; p.bias_p = pk->bias_p;
+  p.w_loc = m->w[W_ATT_LOC_CONV]; p.w_ld = m->w[W_ATT_LOC_DENSE]; p.w_v = m->w[W_ATT_V];
+  p.memory = a->memory; p.pm = w.pm; p.mem_len = a->memory_lengths;
+  p.prenet_keep = a->prenet_keep; p.att_keep = a->att_keep; p.dec_keep = a->dec_keep;
+  p.mel = a->mel; p.gate = a->gate; p.align = a->align; p.mel_lengths = a->mel_lengths; p.n_steps = a->n_steps;
+  p.ctrl = w.ctrl;
+  p.B = B; p.T = T; p.cap = cap; p.infer = a->mode == T2_MODE_INFER; p.training = a->training; p.passes = 3;
+  p.gate_threshold = a->gate_threshold; p.score_mask_value = a->score_mask_value;
+  p.p_att = m->cfg.p_attention_dropout; p.p_dec = m->cfg.p_decoder_dropout; p.seed = a->seed;
+  if (!p.infer) {
+    return fail(T2_ERR_UNSUPPORTED, "persistent decoder: teacher-forced mode needs the x2 image pre-pass (not wired)");
+  }
+  const size_t smem = persistent_smem_bytes(T);
+  T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&p};
+  T2_CUDA(cudaLaunchCooperativeKernel((void*)decoder_persistent_kernel, dim3(kG), dim3(kThreads), args, smem, s));
+  g_launch_count++;
+  return T2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// self test of the tcgen05 engine: C (64 x N) = A (64 x K) . W (N x K)^T with the same run_event()
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(kThreads, 1)
+selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int chunks, int passes, float* C, int N,
+                DecoderCtrl* ctrl) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sp = smem_raw;
+  Ring rg;
+  rg.stage0 = sp; sp += kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
+  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
+  rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
+    ptx::mbar_init(rg.acc, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // run twice: the second run accumulates on top of the first (exercises the accumulate flag and
+  // the ring wrap-around); the host compares against 2 * A.W^T
+  run_event(rg, ep, x_img, w_img, chunks, 1u, passes, tmem_base, ctrl);
+  ptx::tc_fence_before();
+  __syncthreads();
+  run_event(rg, ep, x_img, w_img, chunks, 0u, passes, tmem_base, ctrl);
+  const int quad = warp & 3, cg = warp >> 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
+    float g[8];
+    ptx::tmem_ld8(t_lane + c0, g);
+    if (lane < 16)
+      for (int j = 0; j < 8; ++j) C[(quad * 16 + lane) * N + c0 + j] = g[j];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+}  // namespace
+
+namespace {
+__global__ void selftest_pack_w_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ wimg) {
+  const int chunk = blockIdx.x;
+  __half* hi = reinterpret_cast<__half*>(wimg + (size_t)chunk * N * 256);
+  __half* lo = hi + N * 64;
+  for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    __half h, l;
+    split_fp16(W[(long)r * K + chunk * 64 + k], h, l);
+    const uint32_t e = img_elem_offset(r, k);
+    hi[e] = h; lo[e] = l;
+  }
+}
+}  // namespace
+
+int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s) {
+  if (N % 8 != 0 || N < 8 || N > 64 || K % kChunkK != 0 || K <= 0) return fail(T2_ERR_INVALID, "selftest_umma: N in {8..64 step 8}, K %% 64 == 0");
+  const int chunks = K / kChunkK;
+  uint8_t *ximg = nullptr, *wimg = nullptr; DecoderCtrl* ctrl = nullptr;
+  T2_CUDA(cudaMalloc((void**)&ximg, (size_t)chunks * kXChunkBytes));
+  T2_CUDA(cudaMalloc((void**)&wimg, (size_t)chunks * N * 256));
+  T2_CUDA(cudaMalloc((void**)&ctrl, sizeof(DecoderCtrl)));
+  T2_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(DecoderCtrl), s));
+  CtaPlan hp; memset(&hp, 0, sizeof(hp));
+  hp.ev[0].ncons = 1; hp.ev[0].n[0] = N; hp.ev[0].col[0] = 0; hp.ev[0].w_bytes = N * 256; hp.ev[0].w_off = 0;
+  rows_to_image_kernel<<<dim3(chunks, 1), 256, 0, s>>>(A, K, kRows, K, 0, ximg, 0);
+  T2_LAUNCH_CHECK();
+  selftest_pack_w_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
+  T2_LAUNCH_CHECK();
+  const size_t smem = (size_t)kStages * kStageBytes + 16 * 8 + 64;
+  T2_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_kernel<<<1, kThreads, smem, s>>>(ximg, wimg, hp.ev[0], chunks, passes, C, N, ctrl);
+  T2_LAUNCH_CHECK();
+  T2_CUDA(cudaStreamSynchronize(s));
+  cudaFree(ximg); cudaFree(wimg); cudaFree(ctrl);
+  return T2_OK;
+}
+
+}  // namespace t2

@@ -1,0 +1,357 @@
+"""The reference's nn.Module surface (model.py) over the B200 engine.
+
+Same class names, constructor signatures, attribute names, parameter registration order (hence the
+same ``state_dict`` keys AND the same random initialisation under a given torch seed) as
+NVIDIA/tacotron2 ``model.py`` -- so ``train.py`` / ``inference.ipynb`` / published checkpoints work
+unchanged -- but ``forward`` / ``inference`` run hand-written sm_100a kernels through libt2b200.so:
+
+    Tacotron2.inference  (model.py:517-529)  -> encoder kernels -> persistent decoder kernel -> postnet
+    Tacotron2.forward    (model.py:499-515)  -> encoder -> teacher-forced decoder -> postnet -> parse_output
+    Decoder.inference    (model.py:418-454)  -> t2_decoder_run(INFER): batched, per-row stop latch
+    Decoder.forward      (model.py:381-416)  -> t2_prenet_forward + t2_decoder_run(TEACHER)
+    Encoder.forward/.inference (:173-201), Postnet.forward (:141-146)
+
+There is no CPU path: calling these on CPU tensors raises.
+"""
+import weakref
+from math import sqrt
+
+import torch
+from torch import nn
+
+from . import _capi
+from ._engine import Engine, current_masks
+from .layers import ConvNorm, LinearNorm
+from .utils import get_mask_from_lengths, to_gpu
+
+
+class LocationLayer(nn.Module):
+    """model.py:10-26 (parameters only; evaluated inside the decoder kernels)."""
+
+    def __init__(self, attention_n_filters, attention_kernel_size, attention_dim):
+        super(LocationLayer, self).__init__()
+        padding = int((attention_kernel_size - 1) / 2)
+        self.location_conv = ConvNorm(2, attention_n_filters, kernel_size=attention_kernel_size,
+                                      padding=padding, bias=False, stride=1, dilation=1)
+        self.location_dense = LinearNorm(attention_n_filters, attention_dim, bias=False, w_init_gain='tanh')
+
+
+class Attention(nn.Module):
+    """model.py:29-86 (parameters + score_mask_value, which train.py:76 overwrites from outside)."""
+
+    def __init__(self, attention_rnn_dim, embedding_dim, attention_dim, attention_location_n_filters,
+                 attention_location_kernel_size):
+        super(Attention, self).__init__()
+        self.query_layer = LinearNorm(attention_rnn_dim, attention_dim, bias=False, w_init_gain='tanh')
+        self.memory_layer = LinearNorm(embedding_dim, attention_dim, bias=False, w_init_gain='tanh')
+        self.v = LinearNorm(attention_dim, 1, bias=False)
+        self.location_layer = LocationLayer(attention_location_n_filters, attention_location_kernel_size,
+                                            attention_dim)
+        self.score_mask_value = -float("inf")
+
+
+class _EngineOwner(object):
+    """Mixin: finds (or lazily creates) the Engine for this module.  Sub-modules of a Tacotron2 share
+    the root's engine; a stand-alone Encoder / Decoder / Postnet builds its own (the weight-table
+    entries it does not have are filled with zeros)."""
+
+    _t2_prefix = ""
+
+    def _t2_root(self):
+        ref = self.__dict__.get("_t2_root_ref")
+        root = ref() if ref is not None else None
+        return root if root is not None else self
+
+    def _t2_engine(self):
+        root = self._t2_root()
+        eng = root.__dict__.get("_t2_engine_obj")
+        if eng is None:
+            eng = Engine(root._t2_hparams)
+            root.__dict__["_t2_engine_obj"] = eng
+        prefix = root._t2_prefix
+        if "_t2_hparams" not in root.__dict__:
+            raise RuntimeError("tacotron2_b200: %s must be used as part of a Decoder / Tacotron2" % type(self).__name__)
+        named = {}
+        for k, v in root.named_parameters():
+            named[prefix + k] = v
+        for k, v in root.named_buffers():
+            named[prefix + k] = v
+        eng.ensure(named)
+        return eng
+
+    def _t2_out_dtype(self):
+        for p_ in self.parameters():
+            return p_.dtype
+        return torch.float32
+
+
+def _require_no_grad(module, what):
+    if torch.is_grad_enabled() and any(p_.requires_grad for p_ in module.parameters()):
+        raise NotImplementedError(
+            "tacotron2_b200: %s under autograd is not implemented in this round (forward-only "
+            "engine); wrap the call in torch.no_grad()" % what)
+
+
+class Prenet(nn.Module, _EngineOwner):
+    """model.py:89-100.  Dropout(0.5) is always on, as in the reference (model.py:99)."""
+    _t2_prefix = "decoder.prenet."
+
+    def __init__(self, in_dim, sizes):
+        super(Prenet, self).__init__()
+        in_sizes = [in_dim] + sizes[:-1]
+        self.layers = nn.ModuleList(
+            [LinearNorm(in_size, out_size, bias=False) for (in_size, out_size) in zip(in_sizes, sizes)])
+
+    def forward(self, x):
+        _require_no_grad(self, "Prenet.forward")
+        eng = self._t2_engine()
+        shp = x.shape
+        keep = current_masks()["prenet"]
+        if keep is not None:   # (steps, 2, B, 256) -> (2, steps*B, 256)
+            keep = keep.permute(1, 0, 2, 3).reshape(2, -1, keep.shape[-1])
+        out = eng.prenet(x.reshape(-1, shp[-1]), keep)
+        return out.reshape(*shp[:-1], out.shape[-1]).to(x.dtype)
+
+
+class Postnet(nn.Module, _EngineOwner):
+    """model.py:103-146: five conv1d(k=5) + BatchNorm1d, tanh on the first four."""
+    _t2_prefix = "postnet."
+
+    def __init__(self, hparams):
+        super(Postnet, self).__init__()
+        self.__dict__["_t2_hparams"] = hparams
+        self.convolutions = nn.ModuleList()
+        self.convolutions.append(
+            nn.Sequential(
+                ConvNorm(hparams.n_mel_channels, hparams.postnet_embedding_dim,
+                         kernel_size=hparams.postnet_kernel_size, stride=1,
+                         padding=int((hparams.postnet_kernel_size - 1) / 2), dilation=1, w_init_gain='tanh'),
+                nn.BatchNorm1d(hparams.postnet_embedding_dim)))
+        for i in range(1, hparams.postnet_n_convolutions - 1):
+            self.convolutions.append(
+                nn.Sequential(
+                    ConvNorm(hparams.postnet_embedding_dim, hparams.postnet_embedding_dim,
+                             kernel_size=hparams.postnet_kernel_size, stride=1,
+                             padding=int((hparams.postnet_kernel_size - 1) / 2), dilation=1, w_init_gain='tanh'),
+                    nn.BatchNorm1d(hparams.postnet_embedding_dim)))
+        self.convolutions.append(
+            nn.Sequential(
+                ConvNorm(hparams.postnet_embedding_dim, hparams.n_mel_channels,
+                         kernel_size=hparams.postnet_kernel_size, stride=1,
+                         padding=int((hparams.postnet_kernel_size - 1) / 2), dilation=1, w_init_gain='linear'),
+                nn.BatchNorm1d(hparams.n_mel_channels)))
+
+    def _run(self, x, lengths, add_residual):
+        _require_no_grad(self, "Postnet.forward")
+        eng = self._t2_engine()
+        xt = x.transpose(1, 2)                       # (B, T, 80): the decoder's native storage
+        if xt.dtype != torch.float32 or xt.stride(2) != 1 or xt.stride(1) != xt.shape[2]:
+            xt = xt.float().contiguous()
+        return eng.postnet(xt, lengths, add_residual, self.training, current_masks()["post"]).to(x.dtype)
+
+    def forward(self, x):
+        """x (B, n_mel, T) -> postnet(x) (B, n_mel, T); the caller adds the residual (model.py:511)."""
+        return self._run(x, None, False)
+
+
+class Encoder(nn.Module, _EngineOwner):
+    """model.py:149-201: 3 x (conv1d k5 + BatchNorm1d + ReLU [+dropout]) then a BiLSTM."""
+    _t2_prefix = "encoder."
+
+    def __init__(self, hparams):
+        super(Encoder, self).__init__()
+        self.__dict__["_t2_hparams"] = hparams
+        convolutions = []
+        for _ in range(hparams.encoder_n_convolutions):
+            conv_layer = nn.Sequential(
+                ConvNorm(hparams.encoder_embedding_dim, hparams.encoder_embedding_dim,
+                         kernel_size=hparams.encoder_kernel_size, stride=1,
+                         padding=int((hparams.encoder_kernel_size - 1) / 2), dilation=1, w_init_gain='relu'),
+                nn.BatchNorm1d(hparams.encoder_embedding_dim))
+            convolutions.append(conv_layer)
+        self.convolutions = nn.ModuleList(convolutions)
+        self.lstm = nn.LSTM(hparams.encoder_embedding_dim, int(hparams.encoder_embedding_dim / 2), 1,
+                            batch_first=True, bidirectional=True)
+
+    def _run(self, x, lengths):
+        _require_no_grad(self, "Encoder.forward")
+        eng = self._t2_engine()
+        emb = x.transpose(1, 2)                      # (B, T, 512) -- contiguous when x came from the embedding
+        out = eng.encoder(embedded=emb, lengths=lengths, training=self.training, keep=current_masks()["enc"])
+        return out.to(x.dtype)
+
+    def forward(self, x, input_lengths):
+        """x (B, 512, T) embedded text, input_lengths sorted descending (pack_padded_sequence
+        semantics, model.py:180-188) -> (B, T, 512)."""
+        return self._run(x, input_lengths)
+
+    def inference(self, x):
+        return self._run(x, None)
+
+
+class Decoder(nn.Module, _EngineOwner):
+    """model.py:204-454."""
+    _t2_prefix = "decoder."
+
+    def __init__(self, hparams):
+        super(Decoder, self).__init__()
+        self.__dict__["_t2_hparams"] = hparams
+        self.n_mel_channels = hparams.n_mel_channels
+        self.n_frames_per_step = hparams.n_frames_per_step
+        self.encoder_embedding_dim = hparams.encoder_embedding_dim
+        self.attention_rnn_dim = hparams.attention_rnn_dim
+        self.decoder_rnn_dim = hparams.decoder_rnn_dim
+        self.prenet_dim = hparams.prenet_dim
+        self.max_decoder_steps = hparams.max_decoder_steps
+        self.gate_threshold = hparams.gate_threshold
+        self.p_attention_dropout = hparams.p_attention_dropout
+        self.p_decoder_dropout = hparams.p_decoder_dropout
+
+        self.prenet = Prenet(hparams.n_mel_channels * hparams.n_frames_per_step,
+                             [hparams.prenet_dim, hparams.prenet_dim])
+        self.attention_rnn = nn.LSTMCell(hparams.prenet_dim + hparams.encoder_embedding_dim,
+                                         hparams.attention_rnn_dim)
+        self.attention_layer = Attention(hparams.attention_rnn_dim, hparams.encoder_embedding_dim,
+                                         hparams.attention_dim, hparams.attention_location_n_filters,
+                                         hparams.attention_location_kernel_size)
+        self.decoder_rnn = nn.LSTMCell(hparams.attention_rnn_dim + hparams.encoder_embedding_dim,
+                                       hparams.decoder_rnn_dim, 1)
+        self.linear_projection = LinearNorm(hparams.decoder_rnn_dim + hparams.encoder_embedding_dim,
+                                            hparams.n_mel_channels * hparams.n_frames_per_step)
+        self.gate_layer = LinearNorm(hparams.decoder_rnn_dim + hparams.encoder_embedding_dim, 1,
+                                     bias=True, w_init_gain='sigmoid')
+        self.mel_lengths = None        # (B,) int32 after inference(): frames per row (stop latch)
+        self.prenet.__dict__["_t2_root_ref"] = weakref.ref(self)
+
+    def get_go_frame(self, memory):
+        """model.py:243-256."""
+        return memory.new_zeros(memory.size(0), self.n_mel_channels * self.n_frames_per_step)
+
+    def parse_decoder_inputs(self, decoder_inputs):
+        """model.py:291-309: (B, n_mel, T_out) -> (T_out, B, n_mel)."""
+        decoder_inputs = decoder_inputs.transpose(1, 2)
+        decoder_inputs = decoder_inputs.view(decoder_inputs.size(0),
+                                             int(decoder_inputs.size(1) / self.n_frames_per_step), -1)
+        return decoder_inputs.transpose(0, 1)
+
+    def forward(self, memory, decoder_inputs, memory_lengths):
+        """Teacher-forced pass (model.py:381-416).  Returns mel (B, n_mel, T), gate (B, T),
+        alignments (B, T, T_enc)."""
+        _require_no_grad(self, "Decoder.forward")
+        eng = self._t2_engine()
+        masks = current_masks()
+        B = memory.size(0)
+        go = self.get_go_frame(memory).unsqueeze(0)
+        frames = torch.cat((go.float(), self.parse_decoder_inputs(decoder_inputs).float()), dim=0)   # (T+1, B, 80)
+        T_mel = frames.size(0) - 1
+        pk = masks["prenet"]
+        if pk is not None:
+            pk = pk.permute(1, 0, 2, 3).reshape(2, -1, pk.shape[-1])
+        px = eng.prenet(frames.reshape(-1, frames.size(-1)), pk)                                     # model.py:399
+        smv = float(self.attention_layer.score_mask_value)
+        mel, gate, align, _, _ = eng.decoder(
+            memory, _capi.MODE_TEACHER, T_mel, memory_lengths=memory_lengths, teacher_prenet=px,
+            training=self.training, att_keep=masks["att"], dec_keep=masks["dec"], score_mask_value=smv)
+        dt = memory.dtype
+        return mel.transpose(1, 2).to(dt), gate.to(dt), align.to(dt)
+
+    def inference(self, memory):
+        """Free-running pass (model.py:418-454), batched: per-row stop latch, see README "batched
+        inference".  Returns mel (B, n_mel, T), gate (B, T, 1), alignments (B, T, T_enc); T = steps
+        until every row has fired (or max_decoder_steps); ``self.mel_lengths`` holds per-row lengths."""
+        eng = self._t2_engine()
+        mel, gate, align, lengths, n_steps = eng.decoder(
+            memory, _capi.MODE_INFER, self.max_decoder_steps, prenet_keep=current_masks()["prenet"],
+            gate_threshold=self.gate_threshold)
+        n = int(n_steps.item())                      # the one host sync of the whole loop (model.py:443 syncs every step)
+        self.mel_lengths = lengths
+        if n == self.max_decoder_steps and bool((lengths >= n).any()):
+            fired = torch.sigmoid(gate[:, n - 1]) > self.gate_threshold
+            if not bool(fired.all()):
+                print("Warning! Reached max decoder steps")                                         # model.py:446
+        dt = memory.dtype
+        return (mel[:, :n].transpose(1, 2).to(dt), gate[:, :n].unsqueeze(-1).to(dt), align[:, :n].to(dt))
+
+
+class Tacotron2(nn.Module, _EngineOwner):
+    """model.py:457-529."""
+
+    def __init__(self, hparams):
+        super(Tacotron2, self).__init__()
+        self.__dict__["_t2_hparams"] = hparams
+        self.mask_padding = hparams.mask_padding
+        self.fp16_run = hparams.fp16_run
+        self.n_mel_channels = hparams.n_mel_channels
+        self.n_frames_per_step = hparams.n_frames_per_step
+        self.embedding = nn.Embedding(hparams.n_symbols, hparams.symbols_embedding_dim)
+        std = sqrt(2.0 / (hparams.n_symbols + hparams.symbols_embedding_dim))
+        val = sqrt(3.0) * std  # uniform bounds for std
+        self.embedding.weight.data.uniform_(-val, val)
+        self.encoder = Encoder(hparams)
+        self.decoder = Decoder(hparams)
+        self.postnet = Postnet(hparams)
+        ref = weakref.ref(self)
+        for child in (self.encoder, self.decoder, self.postnet, self.decoder.prenet):
+            child.__dict__["_t2_root_ref"] = ref
+        self.mel_lengths = None
+
+    def parse_batch(self, batch):
+        """model.py:473-485."""
+        text_padded, input_lengths, mel_padded, gate_padded, output_lengths = batch
+        text_padded = to_gpu(text_padded).long()
+        input_lengths = to_gpu(input_lengths).long()
+        max_len = torch.max(input_lengths.data).item()
+        mel_padded = to_gpu(mel_padded).float()
+        gate_padded = to_gpu(gate_padded).float()
+        output_lengths = to_gpu(output_lengths).long()
+        return ((text_padded, input_lengths, mel_padded, max_len, output_lengths), (mel_padded, gate_padded))
+
+    def parse_output(self, outputs, output_lengths=None):
+        """model.py:487-497: zero mel / mel_postnet and set gate to 1e3 beyond each row's length."""
+        if self.mask_padding and output_lengths is not None:
+            mask = ~get_mask_from_lengths(output_lengths, outputs[0].size(2))
+            mask = mask.expand(self.n_mel_channels, mask.size(0), mask.size(1))
+            mask = mask.permute(1, 0, 2)
+            outputs[0].data.masked_fill_(mask, 0.0)
+            outputs[1].data.masked_fill_(mask, 0.0)
+            outputs[2].data.masked_fill_(mask[:, 0, :], 1e3)  # gate energies
+        return outputs
+
+    def forward(self, inputs):
+        """model.py:499-515."""
+        _require_no_grad(self, "Tacotron2.forward")
+        text_inputs, text_lengths, mels, max_len, output_lengths = inputs
+        text_lengths, output_lengths = text_lengths.data, output_lengths.data
+        eng = self._t2_engine()
+        masks = current_masks()
+        memory = eng.encoder(text=text_inputs, lengths=text_lengths, training=self.training, keep=masks["enc"])
+        mel_outputs, gate_outputs, alignments = self.decoder(memory, mels, memory_lengths=text_lengths)
+        mel_btc = mel_outputs.transpose(1, 2)
+        if mel_btc.dtype != torch.float32 or not mel_btc.is_contiguous():
+            mel_btc = mel_btc.float().contiguous()
+        mel_outputs_postnet = eng.postnet(mel_btc, None, True, self.training, masks["post"]).to(mel_outputs.dtype)
+        if self.training:
+            for mod in self.modules():
+                if isinstance(mod, nn.BatchNorm1d) and mod.num_batches_tracked is not None:
+                    mod.num_batches_tracked += 1
+        return self.parse_output([mel_outputs, mel_outputs_postnet, gate_outputs, alignments], output_lengths)
+
+    def inference(self, inputs):
+        """model.py:517-529, batched.  For B > 1 frames at t >= mel_lengths[b] of mel_outputs and
+        mel_outputs_postnet are zero (same convention as parse_output); ``self.mel_lengths`` holds
+        the per-row lengths.  B == 1 is exactly the reference."""
+        eng = self._t2_engine()
+        memory = eng.encoder(text=inputs, lengths=None, training=self.training, keep=current_masks()["enc"])
+        mel_outputs, gate_outputs, alignments = self.decoder.inference(memory)
+        lengths = self.decoder.mel_lengths
+        self.mel_lengths = lengths
+        mel_btc = mel_outputs.transpose(1, 2)
+        if mel_btc.dtype != torch.float32:
+            mel_btc = mel_btc.float().contiguous()
+        multi = inputs.size(0) > 1
+        mel_outputs_postnet = eng.postnet(mel_btc, lengths if multi else None, True, self.training,
+                                          current_masks()["post"]).to(mel_outputs.dtype)
+        if multi:
+            pad = ~get_mask_from_lengths(lengths.long(), mel_outputs.size(2))
+            mel_outputs = mel_outputs.masked_fill(pad.unsqueeze(1), 0.0)
+        return self.parse_output([mel_outputs, mel_outputs_postnet, gate_outputs, alignments])

@@ -1,0 +1,118 @@
+"""CPU: the drop-in boundary -- nn.Module surface (state_dict keys / shapes / initialisation),
+TF-free hparams, the C-ABI library loads and exports every symbol include/t2b200.h declares, the
+ctypes structs match the C layout, and the product path fails loudly without CUDA tensors."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import tacotron2_b200 as t2
+from tacotron2_b200 import _capi
+from tacotron2_b200._engine import weight_table_spec
+from tests.common import ROOT, state_dict_shapes, synth_state_dict
+
+
+def _ensure_built():
+    if not os.path.isfile(_capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+
+def test_state_dict_layout_matches_reference_table():
+    model = t2.Tacotron2(t2.create_hparams())
+    sd = model.state_dict()
+    want = state_dict_shapes()
+    assert list(sd.keys()) == list(want.keys())
+    assert len(sd) == 84
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(want[k]), k
+    spec = weight_table_spec(t2.create_hparams())
+    assert [n for n, _ in spec] == list(want.keys())
+    assert sum(p.numel() for p in model.parameters()) == 28193153
+
+
+def test_same_seed_same_init_as_reference():
+    from oracle.ref_import import default_hparams, import_reference_model, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    ref = import_reference_model()
+    torch.manual_seed(1234)
+    a = ref.Tacotron2(default_hparams()).state_dict()
+    torch.manual_seed(1234)
+    b = t2.Tacotron2(t2.create_hparams()).state_dict()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_load_state_dict_roundtrip_and_attributes():
+    model = t2.Tacotron2(t2.create_hparams())
+    sd = synth_state_dict(3)
+    model.load_state_dict(sd)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k])
+    # attributes callers poke from outside (train.py:76, inference.ipynb)
+    model.decoder.attention_layer.score_mask_value = -65504.0
+    model.decoder.max_decoder_steps = 7
+    model.decoder.gate_threshold = 0.4
+    assert model.decoder.attention_layer.score_mask_value == -65504.0
+    assert model.eval() is model and model.train() is model
+    fired = []
+    model.register_forward_hook(lambda *a: fired.append(1))   # distributed.py:169-172 relies on this
+
+
+def test_hparams_defaults_and_parse():
+    hp = t2.create_hparams("batch_size=8,fp16_run=True,learning_rate=0.01")
+    assert hp.batch_size == 8 and hp.fp16_run is True and abs(hp.learning_rate - 0.01) < 1e-12
+    assert hp.n_symbols == 148 and hp.max_decoder_steps == 1000 and hp.mask_padding is True
+    with pytest.raises(ValueError):
+        t2.create_hparams("no_such=1")
+
+
+def test_product_path_needs_cuda():
+    model = t2.Tacotron2(t2.create_hparams()).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        model.inference(torch.zeros(1, 5, dtype=torch.long))
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    header = open(os.path.join(ROOT, "include", "t2b200.h")).read()
+    declared = set(re.findall(r"\b(t2_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    L = _capi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.t2_abi_version() == 1
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    """sizeof/offsetof of every args struct as gcc sees the header == the ctypes mirror."""
+    src = tmp_path / "layout.c"
+    fields = {
+        "T2Config": ["n_mel_channels", "postnet_n_convolutions", "p_attention_dropout", "bn_eps"],
+        "T2EncoderArgs": ["text", "embedded", "lengths", "B", "T", "training", "keep", "seed", "memory", "ws", "ws_bytes"],
+        "T2DecoderArgs": ["mode", "impl", "training", "memory", "memory_lengths", "B", "T_enc", "n_steps_cap",
+                          "teacher_prenet", "prenet_keep", "att_keep", "dec_keep", "seed", "gate_threshold",
+                          "score_mask_value", "mel", "gate", "align", "mel_lengths", "n_steps", "ws", "ws_bytes"],
+        "T2PostnetArgs": ["mel", "mel_batch_stride", "lengths", "B", "T", "training", "keep", "seed",
+                          "add_residual", "mel_post", "ws", "ws_bytes"],
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "t2b200.h"', 'int main(void){']
+    for s, fs in fields.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
+        for f in fs:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (s, f, s, f))
+    lines.append('return 0;}')
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for s, fs in fields.items():
+        cls = getattr(_capi, s)
+        assert int(out[s]) == ctypes.sizeof(cls), s
+        for f in fs:
+            assert int(out["%s.%s" % (s, f)]) == getattr(cls, f).offset, (s, f)

@@ -1,0 +1,168 @@
+"""GPU (B200): the CUDA path through the public nn.Module API / C-ABI vs (a) the golden vectors
+produced by the reference model.py and (b) the CPU oracle on fresh seeded inputs.
+
+Tolerance (north_star): mel frames within 1e-3 relative fp32 -- measured as max|a-b| / max|b| --
+and stop decisions (mel_lengths) bit-exact.  The engine is expected to land ~1e-5."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import tacotron2_b200 as t2
+from oracle import tacotron2_oracle as O
+from tacotron2_b200 import _capi
+from tests.common import keep_mask, rand_text, rel_err, synth_state_dict
+from tests.test_oracle_golden import INFER, forward_inputs, infer_inputs, load
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+IMPLS = [(_capi.IMPL_STEPWISE, "stepwise"), (_capi.IMPL_PERSISTENT, "persistent")]
+
+
+def make_model(sd, max_steps=None, impl=None, training=False):
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda().train(training)
+    if max_steps is not None:
+        model.decoder.max_decoder_steps = max_steps
+    if impl is not None:
+        model._t2_engine().impl = impl
+    return model
+
+
+def test_native_library_is_loaded():
+    L = _capi.lib()
+    info = (C.c_int32 * 5)()
+    _capi.check(L.t2_device_info(info))
+    assert info[1] == 10, "sm_100 device expected, got sm_%d%d" % (info[1], info[2])
+
+
+@pytest.mark.parametrize("passes,tol", [(3, 2e-6), (1, 2e-3)])
+@pytest.mark.parametrize("N,K", [(32, 256), (8, 64), (64, 1024), (72 - 8, 192)])
+def test_umma_split_gemm_selftest(N, K, passes, tol):
+    """tcgen05 engine of the persistent decoder: C = 2 * A (64xK) . W (NxK)^T (two accumulating runs)."""
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn(64, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    Cd = torch.full((64, N), float("nan"), device="cuda")
+    _capi.check(_capi.lib().t2_selftest_umma(A.data_ptr(), W.data_ptr(), N, K, passes, Cd.data_ptr(),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = 2.0 * (A.double() @ W.double().t())
+    assert rel_err(Cd, ref) < tol
+
+
+@pytest.mark.parametrize("impl,impl_name", IMPLS)
+@pytest.mark.parametrize("name", INFER)
+def test_inference_matches_reference_golden(name, impl, impl_name):
+    g = load(name)
+    sd, text, keep, S = infer_inputs(g)
+    model = make_model(sd, S, impl)
+    with torch.no_grad(), t2.dropout_masks(prenet=keep):
+        mel, post, gate, align = model.inference(text.cuda())
+    torch.cuda.synchronize()
+    assert model.mel_lengths.cpu().tolist() == g["mel_lengths"].tolist()           # bit-exact stop decisions
+    n = int(g["mel"].shape[2])
+    assert mel.shape[2] == n and gate.shape == (text.shape[0], n, 1)
+    assert rel_err(mel, torch.from_numpy(g["mel_masked"])) < TOL
+    assert rel_err(post, torch.from_numpy(g["mel_post"])) < TOL
+    assert rel_err(gate, torch.from_numpy(g["gate"])) < TOL
+    assert rel_err(align, torch.from_numpy(g["align"])) < TOL
+    live = torch.arange(n)[None, :] < torch.from_numpy(g["mel_lengths"])[:, None]
+    dec_e = (torch.sigmoid(gate[:, :, 0].cpu()) > 0.5)[live]
+    dec_g = (torch.sigmoid(torch.from_numpy(g["gate"])[:, :, 0]) > 0.5)[live]
+    assert torch.equal(dec_e, dec_g)
+
+
+@pytest.mark.parametrize("name,training", [("forward_eval_b4", False), ("forward_train_b4", True)])
+def test_teacher_forced_forward_matches_reference_golden(name, training):
+    g = load(name)
+    sd, text, tl, ol, mels, m = forward_inputs(g)
+    model = make_model(sd, training=training)
+    post_keep = [m["qk4"][i] for i in range(4)] + [m["qk1"]]
+    with torch.no_grad(), t2.dropout_masks(prenet=m["pk"], att=m["ak"], dec=m["dk"], enc=m["ek"], post=post_keep):
+        out = model((text.cuda(), tl.cuda(), mels.cuda(), int(tl.max()), ol.cuda()))
+    torch.cuda.synchronize()
+    for a, k in zip(out, ("mel", "mel_post", "gate", "align")):
+        assert rel_err(a, torch.from_numpy(g[k])) < TOL, k
+    if training:   # BatchNorm running statistics were updated like nn.BatchNorm1d does
+        sd_after = model.state_dict()
+        assert rel_err(sd_after["encoder.convolutions.0.1.running_mean"], torch.from_numpy(g["bn0_running_mean"])) < 1e-4
+        assert rel_err(sd_after["encoder.convolutions.0.1.running_var"], torch.from_numpy(g["bn0_running_var"])) < 1e-4
+
+
+def test_encoder_and_postnet_modules_vs_oracle():
+    sd = synth_state_dict(9, scale=1.5)
+    model = make_model(sd)
+    g = torch.Generator().manual_seed(0)
+    B, T = 5, 33
+    text = rand_text(B, T, 2)
+    lengths = torch.tensor([33, 30, 21, 9, 1])
+    emb = sd["embedding.weight"][text].transpose(1, 2)
+    with torch.no_grad():
+        ref_inf = O.encoder(sd, emb, None)
+        ref_fwd = O.encoder(sd, emb, lengths)
+        got_inf = model.encoder.inference(emb.cuda())
+        got_fwd = model.encoder(emb.cuda(), lengths.cuda())
+        assert rel_err(got_inf, ref_inf) < 1e-4 and rel_err(got_fwd, ref_fwd) < 1e-4
+        assert float(got_fwd[3, 9:].abs().max()) == 0.0                        # zeros at padded positions
+        x = torch.randn(3, 80, 41, generator=g)
+        assert rel_err(model.postnet(x.cuda()), O.postnet(sd, x)) < 1e-4
+
+
+@pytest.mark.parametrize("impl,impl_name", IMPLS)
+def test_fresh_inputs_vs_oracle_edge_shapes(impl, impl_name):
+    """Ragged / minimal shapes: B=1 T_text=1, odd T_text, B not a multiple of anything."""
+    for (B, T, S, seed) in [(1, 1, 5, 1), (7, 13, 9, 2), (2, 150, 6, 3)]:
+        sd = synth_state_dict(100 + seed, gate_bias=-10.0, scale=2.0)
+        model = make_model(sd, S, impl)
+        text = rand_text(B, T, seed)
+        keep = keep_mask((S, 2, B, 256), 0.5, seed + 50)
+        with torch.no_grad():
+            ref = O.tacotron2_inference(sd, text, keep, 0.5, S)
+            with t2.dropout_masks(prenet=keep):
+                out = model.inference(text.cuda())
+        assert model.mel_lengths.cpu().tolist() == ref[4].tolist()
+        for a, b in zip(out, (ref[0], ref[1], ref[2], ref[3])):
+            assert rel_err(a, b) < TOL, (B, T, impl_name)
+
+
+def test_full_size_persistent_vs_stepwise_and_oracle_prefix():
+    """BASELINE config 2 shape (B=64, T_text=150): the two CUDA implementations agree over 200 steps
+    and match the CPU oracle on the first 24 (the oracle costs ~8 ms per step at this size)."""
+    B, T, S = 64, 150, 200
+    sd = synth_state_dict(1234, gate_bias=-10.0, scale=2.0)
+    text = rand_text(B, T, 7)
+    keep = keep_mask((S, 2, B, 256), 0.5, 8)
+    outs = {}
+    for impl, nm in IMPLS:
+        model = make_model(sd, S, impl)
+        with torch.no_grad(), t2.dropout_masks(prenet=keep):
+            outs[nm] = [o.cpu() for o in model.inference(text.cuda())]
+        assert model.mel_lengths.cpu().tolist() == [S] * B
+    for a, b in zip(outs["persistent"], outs["stepwise"]):
+        assert rel_err(a, b) < TOL
+    with torch.no_grad():
+        memory = O.encoder(sd, sd["embedding.weight"][text].transpose(1, 2))
+        ref = O.decoder_inference(sd, memory, keep, 0.5, 24)
+    assert rel_err(outs["persistent"][0][:, :, :24], ref[0]) < TOL
+    assert rel_err(outs["persistent"][3][:, :24], ref[2]) < TOL
+    # size-independent properties: attention rows are probability vectors, alignments non-negative
+    al = outs["persistent"][3]
+    assert float((al.sum(-1) - 1).abs().max()) < 1e-4 and float(al.min()) >= 0.0
+
+
+def test_philox_mode_is_deterministic_and_statistically_sane():
+    """Production dropout (no injected masks): same seed -> same output on both implementations."""
+    sd = synth_state_dict(77, gate_bias=-10.0, scale=2.0)
+    text = rand_text(3, 21, 5).cuda()
+    res = []
+    for impl, nm in IMPLS:
+        model = make_model(sd, 10, impl)
+        import tacotron2_b200._engine as E
+        E._seed_counter[0] = 1000
+        torch.manual_seed(5)
+        with torch.no_grad():
+            res.append(model.inference(text)[0].cpu())
+    assert rel_err(res[0], res[1]) < TOL
