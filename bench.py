@@ -225,6 +225,13 @@ def main():
     barrier()
     ms_dec = timed(decoder_only, args.steps)
     sampler.stop_flag = True
+    phase_profile = None
+    try:
+        prof = eng.decoder_profile()
+        tot = sum(v[0] for v in prof.values()) or 1
+        phase_profile = {k: {"us_per_step_cta0_60_100": [round(x / 1965.0 / T_MEL, 2) for x in v]} for k, v in prof.items()}
+    except Exception as e:  # stepwise implementation has no phase profile
+        phase_profile = {"unavailable": str(e)[:80]}
     n_frames = int(out_host[2][0]) * B_PER_GPU
     assert n_frames == B_PER_GPU * T_MEL, "workload did not produce 800 frames per row: %d" % n_frames
     t = torch.tensor([ms_dev, ms_e2e, ms_dec], device="cuda", dtype=torch.float64)
@@ -262,6 +269,7 @@ def main():
                      "stream_bytes": {"achieved_GBps": ach_gbs, "peak_GBps": peak_gbs, "frac": ach_gbs / peak_gbs,
                                       "bytes_per_step": STREAM_BYTES_PER_STEP}},
         "clocks": sampler.summary(),
+        "decoder_phase_profile": phase_profile,
     }
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_port_sample(os.cpu_count() or 1, dec_steps=60)

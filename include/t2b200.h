@@ -181,6 +181,10 @@ int    t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_
  * (64 x K) x (N x K)^T problem and writes C (64 x N) fp32; used by tests/test_umma_gemm.py. */
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes,
                      float* C, void* stream);
+/* After a T2_IMPL_PERSISTENT run with the same args / workspace: SM cycles spent per phase of the
+ * persistent kernel, summed over steps, on three sample CTAs (out_host[3][16]; phase list in
+ * decoder_persistent.cu).  Synchronises the device. */
+int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t t2_kernel_launch_count(void);
 

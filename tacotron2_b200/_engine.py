@@ -243,7 +243,17 @@ class Engine:
         a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(self.device):
             _capi.check(L.t2_decoder_run(self.handle, C.byref(a), self._stream()))
+        self._last_decoder_args = (a, memory, len32, teacher_prenet, pk, ak, dk, ws, mel, gate, align, mel_lengths, n_steps)
         return mel, gate, align, mel_lengths, n_steps
+
+    def decoder_profile(self):
+        """Per-phase SM cycles of the last persistent decoder run: dict phase -> [cta0, cta60, cta100]."""
+        a = self._last_decoder_args[0]
+        out = (C.c_int64 * 48)()
+        _capi.check(_capi.lib().t2_decoder_profile(C.byref(a), out))
+        names = ["E0 x2->att gemm", "E0 epilogue(ah)", "B1", "E1 ah->dec/att/q gemm", "B2", "attention", "B3",
+                 "E2 ctx gemm", "E2 epilogue(dh)", "B4", "E3 dh gemm", "E3 epilogue(mel/x1)", "B5", "E4 x1 gemm+epi", "B6", "-"]
+        return {names[i]: [int(out[s * 16 + i]) for s in range(3)] for i in range(15)}
 
     def prenet(self, frames, keep=None):
         """frames (M, 80) -> (M, 256); keep (2, M, 256) uint8 or None."""

@@ -320,6 +320,15 @@ int t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_tex
   return T2_OK;
 }
 
+int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host) {
+  if (!a || !out_host) return fail(T2_ERR_INVALID, "decoder_profile: null argument");
+  DecoderWs w;
+  T2_TRY(decoder_ws_carve(a, &w));
+  T2_CUDA(cudaDeviceSynchronize());
+  T2_CUDA(cudaMemcpy(out_host, w.ctrl->prof, sizeof(long long) * 48, cudaMemcpyDeviceToHost));
+  return T2_OK;
+}
+
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes, float* C, void* stream) {
   return selftest_umma(A, W, N, K, passes, C, (cudaStream_t)stream);
 }

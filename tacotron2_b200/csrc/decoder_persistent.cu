@@ -367,12 +367,24 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   const bool has_x2 = cta >= kX2Cta0 && cta < kX2Cta0 + kX2Ctas;
   const bool has_p = cta >= kPCta0 && cta < kPCta0 + kPCtas;
   const int halfk = (kLocK - 1) / 2;
+  // phase profile (cycles, accumulated over steps) on three sample CTAs; see t2_decoder_profile()
+  const int prof_slot = cta == 0 ? 0 : (cta == 60 ? 1 : (cta == 100 ? 2 : -1));
+  long long prof_last = clock64();
+#define T2_PROF(ph)                                                        \
+  do {                                                                     \
+    if (prof_slot >= 0 && tid == 0) {                                      \
+      const long long now_ = clock64();                                    \
+      ctrl->prof[prof_slot][ph] += now_ - prof_last;                       \
+      prof_last = now_;                                                    \
+    }                                                                      \
+  } while (0)
   int t = 0;
   for (; t < p.cap; ++t) {
     // ======== E0: x2_t -> attention LSTM gates, epilogue -> ah_t ==================== model.py:352-356
     {
       const uint8_t* x2 = p.infer ? p.x2_img : p.teacher_x2_img + (size_t)t * 4 * kXChunkBytes;
       run_event(rg, plan.ev[0], x2, p.wimg, 4, t == 0 ? 1u : 0u, p.passes, tmem_base, ctrl);
+      T2_PROF(0);
       float g[8];
       ptx::tmem_ld8(t_lane + kColA + cg * 8, g);
       if (erow) {
@@ -398,7 +410,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
       ptx::tc_fence_before();
+      T2_PROF(1);
       grid_barrier(ctrl, bar_gen);                                             // B1: ah_t complete
+      T2_PROF(2);
     }
     // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
     {
@@ -412,7 +426,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       ptx::tc_fence_before();
+      T2_PROF(3);
       grid_barrier(ctrl, bar_gen);                                             // B2: q complete
+      T2_PROF(4);
     }
     // ======== attention for batch row `cta` ================================== model.py:43-86, 358-365
     if (cta < p.B) {
@@ -487,10 +503,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if ((lane & 1) == 0) store_split2(p.ctx_img, b, col, cv, nb);
       }
     }
+    T2_PROF(5);
     grid_barrier(ctrl, bar_gen);                                               // B3: ctx_t complete
+    T2_PROF(6);
     // ======== E2: ctx_t -> dec gates (rest), next att gates, projection (part); epilogue -> dh_t
     {
       run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, 4u, p.passes, tmem_base, ctrl);
+      T2_PROF(7);
       float g[8];
       ptx::tmem_ld8(t_lane + kColD + cg * 8, g);
       if (erow) {
@@ -516,11 +535,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         store_split2(p.dh_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
       ptx::tc_fence_before();
+      T2_PROF(8);
       grid_barrier(ctrl, bar_gen);                                             // B4: dh_t complete
+      T2_PROF(9);
     }
     // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
     {
       run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, 1u, p.passes, tmem_base, ctrl);
+      T2_PROF(10);
       if (tid == 0) *s_live = 0;
       __syncthreads();
       if (has_p && cg == 0) {
@@ -583,8 +605,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         __threadfence();
       }
       ptx::tc_fence_before();
+      T2_PROF(11);
       if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
       grid_barrier(ctrl, bar_gen);                                             // B5: x1 / stop flag complete
+      T2_PROF(12);
       int all_done;
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
       if (all_done || t + 1 == p.cap) { ++t; break; }
@@ -610,7 +634,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       ptx::tc_fence_before();
+      T2_PROF(13);
       grid_barrier(ctrl, bar_gen);                                             // B6: x2_(t+1) complete
+      T2_PROF(14);
     }
   }
   // rows that never fired: length = number of steps run (model.py:445-447)
