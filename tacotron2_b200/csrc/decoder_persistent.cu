@@ -21,7 +21,9 @@
 //   * location-sensitive attention (model.py:43-86) runs per batch row on CTA b with warp-shuffle
 //     reductions; previous / cumulative attention weights stay in shared memory across steps.
 //   * events are separated by a grid-wide barrier (global atomic counter + generation flag).
-#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <vector>
 
 #include "decoder.h"
@@ -40,8 +42,11 @@ constexpr int kRows = 64;             // MMA M (batch rows, zero padded)
 constexpr int kXChunkBytes = kRows * kChunkK * 2 * 2;   // hi + lo planes = 16 KiB
 constexpr int kWStageMax = 72 * kChunkK * 2 * 2;        // up to 72 W rows per stage = 18 KiB
 constexpr int kStageBytes = kXChunkBytes + kWStageMax;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 512;
 constexpr int kColA = 0, kColD = 32, kColP = 64, kColQ = 72, kColX2 = 80;
+constexpr int kColAtt = 128;          // attention pa accumulators: up to 3 tiles of 128 rows x 128 columns
+constexpr int kMaxAttTiles = 3;       // T_enc <= 384
+constexpr int kWeffBytes = kAtt * kChunkK * 2 * 2;   // fused location filter image (hi+lo) = 32 KiB
 constexpr int kNumEvents = 5;         // x2, ah, ctx, dh, x1
 constexpr int kPCols = 344;           // 80 mel + 1 gate + 256 x1 + 7 pad
 constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 43;
@@ -66,6 +71,8 @@ struct PersistentPack {
   float* bias_a = nullptr;            // (kG, 32) att LSTM bias in TMEM column order
   float* bias_d = nullptr;            // (kG, 32)
   int32_t* rows = nullptr;            // scratch row tables for packing
+  float* weff = nullptr;              // (128, 64) fp32 fused location filter W_ld . W_loc (62 taps + 2 zero)
+  uint8_t* weff_img = nullptr;        // its split-fp16 operand image (32 KiB)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -85,6 +92,33 @@ __global__ void fuse_prenet_proj_kernel(const float* __restrict__ w1, const floa
     float s = 0.f;
     for (int k = 0; k < kMel; ++k) s = fmaf(w1[r * kMel + k], bp[k], s);
     out_b[r] = s;
+  }
+}
+
+// Weff[d][ch*31+k] = sum_c W_ld[d][c] * W_loc[c][ch][k]: location conv (model.py:23) and location dense
+// (model.py:24-25) are both linear, so they fuse into one 62-tap filter bank per attention dimension.
+__global__ void fuse_location_kernel(const float* __restrict__ wld, const float* __restrict__ wloc,
+                                     float* __restrict__ weff) {
+  const int d = blockIdx.x, kk = threadIdx.x;      // 128 x 64
+  float s = 0.f;
+  if (kk < 2 * kLocK) {
+    const int ch = kk / kLocK, k = kk - ch * kLocK;
+    for (int c = 0; c < kLocF; ++c) s = fmaf(wld[d * kLocF + c], wloc[(c * 2 + ch) * kLocK + k], s);
+  }
+  weff[d * kChunkK + kk] = s;
+}
+
+// (N x K) fp32 row-major -> K/64 chunks of [hi plane | lo plane] (N rows each) in the canonical layout
+__global__ void pack_rows_image_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ wimg) {
+  const int chunk = blockIdx.x;
+  __half* hi = reinterpret_cast<__half*>(wimg + (size_t)chunk * N * 256);
+  __half* lo = hi + N * 64;
+  for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    __half h, l;
+    split_fp16(W[(long)r * K + chunk * 64 + k], h, l);
+    const uint32_t e = img_elem_offset(r, k);
+    hi[e] = h; lo[e] = l;
   }
 }
 
@@ -155,30 +189,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Decode
   }
 }
 
-// grid-wide barrier: counter + generation (release / acquire at gpu scope).  Also orders the generic
-// proxy stores of the epilogues before the async-proxy (bulk copy) reads of the next event.
-__device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& gen) {
+// grid-wide barrier: one monotonically increasing arrival counter; arrive = red.release, wait = poll with
+// ld.acquire until the counter reaches this barrier's target (no reset / generation hop).  Also orders
+// the generic-proxy stores of the epilogues before the async-proxy (bulk copy) reads of the next event.
+__device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& target) {
   ptx::fence_proxy_async();
   __syncthreads();
+  target += gridDim.x;
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int prev = atomicAdd(&ctrl->bar_count, 1u);
-    if (prev == gridDim.x - 1) {
-      ctrl->bar_count = 0;
-      __threadfence();
-      atomicExch(&ctrl->bar_gen, gen + 1);
-    } else {
-      const unsigned long long t0 = clock64();
-      while (true) {
-        unsigned int g;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(&ctrl->bar_gen) : "memory");
-        if (g != gen) break;
-        if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 100);
-      }
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
+    const unsigned long long t0 = clock64();
+    while (true) {
+      unsigned int c;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->bar_count) : "memory");
+      if ((int)(c - target) >= 0) break;
+      if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 100);
     }
-    __threadfence();
   }
-  gen += 1;
   __syncthreads();
   ptx::fence_proxy_async();
 }
@@ -206,6 +234,7 @@ struct Ring {
   uint32_t p_stage, p_phase;   // producer cursor (thread 0 of warp 0)
   uint32_t c_stage, c_phase;   // consumer cursor (thread 0 of warp 1)
   uint32_t acc_phase;          // all threads
+  uint64_t pol_x, pol_w;       // L2 eviction policies of the activation / weight streams
 };
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight slices through the
@@ -221,9 +250,9 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
         mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
         uint8_t* st = rg.stage(rg.p_stage);
         ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
-        ptx::bulk_g2s(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage]);
-        ptx::bulk_g2s(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
-                      &rg.full[rg.p_stage]);
+        ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
+        ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
+                           &rg.full[rg.p_stage], rg.pol_w);
         if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
       }
     }
@@ -273,7 +302,8 @@ struct KParams {
   const uint8_t* wimg;
   const float* bias_a; const float* bias_d; const float* bias_p;
   // attention weights (fp32, caller's tensors)
-  const float* w_loc; const float* w_ld; const float* w_v;
+  const uint8_t* weff_img; const float* w_v;
+  float l2_pin_frac;
   // tensors
   const float* memory; const float* pm; const int32_t* mem_len;
   const uint8_t* prenet_keep; const uint8_t* att_keep; const uint8_t* dec_keep;
@@ -322,15 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   int* s_live = reinterpret_cast<int*>(sp); sp += 16;
   float* s_bias_a = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_bias_d = reinterpret_cast<float*>(sp); sp += 32 * 4;
-  float* s_wld_t = reinterpret_cast<float*>(sp); sp += kLocF * kAtt * 4;      // [c][d]
-  float* s_wloc = reinterpret_cast<float*>(sp); sp += kLocF * 2 * kLocK * 4;
   float* s_v = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_q = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
-  float* s_e = reinterpret_cast<float*>(sp); sp += ((T + 3) & ~3) * 4;
-  float* s_loc = reinterpret_cast<float*>(sp);                                // [32][T]
+  const int ntiles = (T + 127) >> 7;
+  float* s_e = reinterpret_cast<float*>(sp); sp += ntiles * 128 * 4;
+  sp = smem_raw + (((sp - smem_raw) + 1023) & ~(size_t)1023);
+  uint8_t* s_weff = sp;                                                       // fused location filter image
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
 
@@ -341,13 +371,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   }
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
   for (int i = tid; i < 32; i += kThreads) { s_bias_a[i] = p.bias_a[cta * 32 + i]; s_bias_d[i] = p.bias_d[cta * 32 + i]; }
-  for (int i = tid; i < kLocF * kAtt; i += kThreads) {
-    const int d = i / kLocF, c = i - d * kLocF;
-    s_wld_t[c * kAtt + d] = p.w_ld[i];
+  for (int i = tid; i < kWeffBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(s_weff)[i] = reinterpret_cast<const uint4*>(p.weff_img)[i];
+  {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(p.l2_pin_frac));
+    rg.pol_w = pol;
+    rg.pol_x = ptx::policy_evict_last();
   }
-  for (int i = tid; i < kLocF * 2 * kLocK; i += kThreads) s_wloc[i] = p.w_loc[i];
   for (int i = tid; i < kAtt; i += kThreads) s_v[i] = p.w_v[i];
   for (int i = tid; i < TP; i += kThreads) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }   // model.py:274-277
+  ptx::fence_proxy_async();       // s_weff is read by tcgen05.mma (async proxy)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -434,36 +468,92 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     if (cta < p.B) {
       const int b = cta;
       for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
-      __syncthreads();
-      for (int i = tid; i < kLocF * T; i += kThreads) {        // location conv          model.py:23
-        const int c = i / T, j = i - c * T;
-        const float* w0 = s_wloc + c * 2 * kLocK;
-        float s = 0.f;
+      for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
+      // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], written as
+      //     split-fp16 canonical tiles of 128 rows into the (idle) operand ring           model.py:23
+      uint8_t* aimg = rg.stage0;
+      for (int item = tid; item < ntiles * 128 * 8; item += kThreads) {
+        const int j = item >> 3, g8 = item & 7;
+        const int tile = j >> 7, r = j & 127;
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
 #pragma unroll
-        for (int k = 0; k < kLocK; ++k) s = fmaf(w0[k], s_pad0[j + k], s);
-#pragma unroll
-        for (int k = 0; k < kLocK; ++k) s = fmaf(w0[kLocK + k], s_pad1[j + k], s);
-        s_loc[i] = s;
+        for (int e = 0; e < 8; ++e) {
+          const int kk = g8 * 8 + e;
+          float v = 0.f;
+          if (kk < 2 * kLocK && j < T) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
+          split_fp16(v, hh[e], ll[e]);
+        }
+        uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + g8 * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
       }
+      ptx::fence_proxy_async();
+      __syncthreads();
+      // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
+      //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
+      if (warp == 1) {
+        if (lane == 0) {
+          ptx::tc_fence_after();
+          const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
+          const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+          for (int tile = 0; tile < ntiles; ++tile) {
+            const uint32_t d = tmem_base + kColAtt + tile * 128;
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              const uint64_t a_hi = ptx::make_smem_desc(as + tile * 32768 + kk * 256, 128, 1024);
+              const uint64_t a_lo = ptx::make_smem_desc(as + tile * 32768 + 16384 + kk * 256, 128, 1024);
+              const uint64_t b_hi = ptx::make_smem_desc(bs + kk * 256, 128, 1024);
+              const uint64_t b_lo = ptx::make_smem_desc(bs + 16384 + kk * 256, 128, 1024);
+              ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
+              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(rg.acc);
+        }
+        __syncwarp();
+      }
+      mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
+      rg.acc_phase ^= 1;
+      ptx::tc_fence_after();
+      // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
+      //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
+      {
+        int nact = 0;
+        for (int tl = 0; tl < ntiles; ++tl)
+          if (tl * 128 + quad * 32 < T) nact = tl + 1;
+        float part = 0.f;
+        int cur_tile = -1;
+        for (int c = cg; c < nact * 16; c += kWarps / 4) {
+          const int tile = c >> 4, col0 = (c & 15) * 8;
+          if (tile != cur_tile) {
+            if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+            part = 0.f; cur_tile = tile;
+          }
+          const int j = tile * 128 + quad * 32 + lane;
+          float g[8];
+          ptx::tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + kColAtt + tile * 128 + col0, g);
+          if (j < T) {
+            const float* pmr = p.pm + ((long)b * T + j) * kAtt + col0;
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(pmr));
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+            const float pmv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
+          }
+        }
+        if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+      }
+      ptx::tc_fence_before();
       __syncthreads();
       const int len = p.mem_len ? p.mem_len[b] : T;
-      for (int j = warp; j < T; j += kWarps) {                 // energies               model.py:58-60
-        float part = 0.f;
-#pragma unroll
-        for (int r = 0; r < kAtt / 32; ++r) {
-          const int d = lane + 32 * r;
-          float pa = 0.f;
-#pragma unroll
-          for (int c = 0; c < kLocF; ++c) pa = fmaf(s_wld_t[c * kAtt + d], s_loc[c * T + j], pa);
-          const float x = s_q[d] + pa + p.pm[((long)b * T + j) * kAtt + d];
-          part = fmaf(s_v[d], tanhf(x), part);
-        }
-        part = warp_sum_f(part);
-        if (lane == 0) s_e[j] = (j < len) ? part : p.score_mask_value;       // model.py:79-80
+      float mx = -INFINITY;                                     // mask + softmax         model.py:79-82
+      for (int j = tid; j < T; j += kThreads) {
+        const float e = (j < len) ? s_e[j] : p.score_mask_value;
+        s_e[j] = e;
+        mx = fmaxf(mx, e);
       }
-      __syncthreads();
-      float mx = -INFINITY;                                     // softmax                model.py:82
-      for (int j = tid; j < T; j += kThreads) mx = fmaxf(mx, s_e[j]);
       mx = warp_max_f(mx);
       if (lane == 0) s_red[warp] = mx;
       __syncthreads();
@@ -488,19 +578,25 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         p.align[((long)b * p.cap + t) * T + j] = a;
       }
       __syncthreads();
-      {                                                           // context                model.py:83-84
-        const int col = tid;                                      // kThreads == kEnc
-        const float* mp = p.memory + (long)b * T * kEnc + col;
-        float s0 = 0.f, s1 = 0.f;
-        int j = 0;
-        for (; j + 1 < T; j += 2) {
-          s0 = fmaf(s_e[j], mp[(long)j * kEnc], s0);
-          s1 = fmaf(s_e[j + 1], mp[(long)(j + 1) * kEnc], s1);
+      {                                                           // context = aw . memory  model.py:83-84
+        float* scr = reinterpret_cast<float*>(rg.stage0);         // [4][512] partial sums (ring is idle)
+        const int c4 = tid & 127, jg = tid >> 7;
+        const float* mp = p.memory + (long)b * T * kEnc + c4 * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int j = jg; j < T; j += 4) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (long)j * kEnc));
+          const float a = s_e[j];
+          acc.x = fmaf(a, m.x, acc.x); acc.y = fmaf(a, m.y, acc.y); acc.z = fmaf(a, m.z, acc.z); acc.w = fmaf(a, m.w, acc.w);
         }
-        if (j < T) s0 = fmaf(s_e[j], mp[(long)j * kEnc], s0);
-        const float cv = s0 + s1;
-        const float nb = __shfl_down_sync(0xffffffffu, cv, 1);
-        if ((lane & 1) == 0) store_split2(p.ctx_img, b, col, cv, nb);
+        *reinterpret_cast<float4*>(scr + jg * kEnc + c4 * 4) = acc;
+        __syncthreads();
+        if (tid < kEnc / 2) {
+          const int col = tid * 2;
+          const float v0 = (scr[col] + scr[kEnc + col]) + (scr[2 * kEnc + col] + scr[3 * kEnc + col]);
+          const float v1 = (scr[col + 1] + scr[kEnc + col + 1]) + (scr[2 * kEnc + col + 1] + scr[3 * kEnc + col + 1]);
+          store_split2(p.ctx_img, b, col, v0, v1);
+        }
       }
     }
     T2_PROF(5);
@@ -659,10 +755,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 // ---------------------------------------------------------------------------------------------
 static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
-  size_t n = (size_t)kStages * kStageBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + (size_t)kLocF * kAtt * 4 +
-             kLocF * 2 * kLocK * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 +
-             (size_t)((T + 3) & ~3) * 4 + (size_t)kLocF * T * 4;
-  return n + 1024;
+  const int ntiles = (T + 127) / 128;
+  size_t n = (size_t)kStages * kStageBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
+             2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4;
+  n = (n + 1023) & ~(size_t)1023;
+  return n + kWeffBytes + 1024;
 }
 
 size_t persistent_ws_bytes(int B, int T) {
@@ -676,6 +773,7 @@ bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
   if (m->sm_count < kG) return false;
   if (a->B > kRows) return false;
   if (a->mode != T2_MODE_INFER) return false;   // teacher forcing runs on the stepwise path for now
+  if (a->T_enc > 128 * kMaxAttTiles) return false;   // TMEM: 128 + 3 x 128 accumulator columns
   if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
   return true;
 }
@@ -715,7 +813,13 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
     T2_CUDA(cudaMalloc((void**)&pk->bias_a, (size_t)kG * 32 * 4));
     T2_CUDA(cudaMalloc((void**)&pk->bias_d, (size_t)kG * 32 * 4));
     T2_CUDA(cudaMalloc((void**)&pk->rows, (size_t)4 * kG * 32 * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->weff, (size_t)kAtt * kChunkK * 4));
+    T2_CUDA(cudaMalloc((void**)&pk->weff_img, (size_t)kWeffBytes));
   }
+  fuse_location_kernel<<<kAtt, kChunkK, 0, s>>>(m->w[W_ATT_LOC_DENSE], m->w[W_ATT_LOC_CONV], pk->weff);
+  T2_LAUNCH_CHECK();
+  pack_rows_image_kernel<<<1, 256, 0, s>>>(pk->weff, kAtt, kChunkK, pk->weff_img);
+  T2_LAUNCH_CHECK();
   T2_CUDA(cudaMemcpyAsync(pk->plans, plans.data(), sizeof(CtaPlan) * kG, cudaMemcpyHostToDevice, s));
   T2_CUDA(cudaStreamSynchronize(s));   // `plans` is a host temporary
   // ---- W_P = [proj (80) ; gate (1) ; W1.Wproj (256) ; 0 (7)] and its bias ----
@@ -764,7 +868,7 @@ void persistent_pack_destroy(T2Model* m) {
   PersistentPack* pk = (PersistentPack*)m->pk;
   if (!pk) return;
   cudaFree(pk->wimg); cudaFree(pk->plans); cudaFree(pk->wp_all); cudaFree(pk->bias_p);
-  cudaFree(pk->bias_a); cudaFree(pk->bias_d); cudaFree(pk->rows);
+  cudaFree(pk->bias_a); cudaFree(pk->bias_d); cudaFree(pk->rows); cudaFree(pk->weff); cudaFree(pk->weff_img);
   delete pk;
   m->pk = nullptr;
 }
@@ -792,7 +896,11 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   p.x1_img = img; img += 4 * kXChunkBytes;
   p.q = (float*)img;
   p.plans = pk->plans; p.wimg = pk->wimg; p.bias_a = pk->bias_a; p.bias_d = pk->bias_d; p.bias_p = pk->bias_p;
-  p.w_loc = m->w[W_ATT_LOC_CONV]; p.w_ld = m->w[W_ATT_LOC_DENSE]; p.w_v = m->w[W_ATT_V];
+  p.weff_img = pk->weff_img; p.w_v = m->w[W_ATT_V];
+  {
+    const char* e = getenv("T2_L2_PIN_FRAC");   // fraction of weight-image lines kept with evict_last priority
+    p.l2_pin_frac = e ? (float)atof(e) : 1.0f;
+  }
   p.memory = a->memory; p.pm = w.pm; p.mem_len = a->memory_lengths;
   p.prenet_keep = a->prenet_keep; p.att_keep = a->att_keep; p.dec_keep = a->dec_keep;
   p.mel = a->mel; p.gate = a->gate; p.align = a->align; p.mel_lengths = a->mel_lengths; p.n_steps = a->n_steps;
@@ -827,6 +935,7 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
+  rg.pol_x = rg.pol_w = ptx::policy_evict_last();
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);
@@ -857,21 +966,6 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
 }
 }  // namespace
 
-namespace {
-__global__ void selftest_pack_w_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ wimg) {
-  const int chunk = blockIdx.x;
-  __half* hi = reinterpret_cast<__half*>(wimg + (size_t)chunk * N * 256);
-  __half* lo = hi + N * 64;
-  for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
-    const int r = i >> 6, k = i & 63;
-    __half h, l;
-    split_fp16(W[(long)r * K + chunk * 64 + k], h, l);
-    const uint32_t e = img_elem_offset(r, k);
-    hi[e] = h; lo[e] = l;
-  }
-}
-}  // namespace
-
 int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s) {
   if (N % 8 != 0 || N < 8 || N > 64 || K % kChunkK != 0 || K <= 0) return fail(T2_ERR_INVALID, "selftest_umma: N in {8..64 step 8}, K %% 64 == 0");
   const int chunks = K / kChunkK;
@@ -884,7 +978,7 @@ int selftest_umma(const float* A, const float* W, int N, int K, int passes, floa
   hp.ev[0].ncons = 1; hp.ev[0].n[0] = N; hp.ev[0].col[0] = 0; hp.ev[0].w_bytes = N * 256; hp.ev[0].w_off = 0;
   rows_to_image_kernel<<<dim3(chunks, 1), 256, 0, s>>>(A, K, kRows, K, 0, ximg, 0);
   T2_LAUNCH_CHECK();
-  selftest_pack_w_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
+  pack_rows_image_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
   T2_LAUNCH_CHECK();
   const size_t smem = (size_t)kStages * kStageBytes + 16 * 8 + 64;
   T2_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -52,6 +52,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// L2 eviction-priority policies for operand streams that are re-read every decoder step
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+
 // ---- tensor memory ------------------------------------------------------------------------------
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {   // one full warp
@@ -104,10 +131,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
-// instruction descriptor kind::f16: D fp32, A/B fp16, both K-major, M = 64
-__device__ __forceinline__ uint32_t make_idesc_f16_m64(uint32_t N) {
-  return (1u << 4) | ((N >> 3) << 17) | ((64u >> 4) << 24);
+// instruction descriptor kind::f16: D fp32, A/B fp16, both K-major
+__device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t make_idesc_f16_m64(uint32_t N) { return make_idesc_f16(64, N); }
 
 }  // namespace ptx
 
