@@ -38,6 +38,7 @@ constexpr int kG = 128;               // CTAs
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
+constexpr int kCluster = 8;            // CTAs per cluster: activation chunks are TMA-multicast to all of them
 constexpr int kRows = 64;             // MMA M (batch rows, zero padded)
 constexpr int kXChunkBytes = kRows * kChunkK * 2 * 2;   // hi + lo planes = 16 KiB
 constexpr int kWStageMax = 72 * kChunkK * 2 * 2;        // up to 72 W rows per stage = 18 KiB
@@ -235,6 +236,7 @@ struct Ring {
   uint32_t c_stage, c_phase;   // consumer cursor (thread 0 of warp 1)
   uint32_t acc_phase;          // all threads
   uint64_t pol_x, pol_w;       // L2 eviction policies of the activation / weight streams
+  uint32_t cs, rank;           // cluster size (1 = no multicast) and this CTA's rank in it
 };
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight slices through the
@@ -250,7 +252,13 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
         mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
         uint8_t* st = rg.stage(rg.p_stage);
         ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
-        ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
+        if (rg.cs == 1) {
+          ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
+        } else {   // every CTA of the cluster fetches 1/cs of the activation chunk and multicasts it to all
+          const uint32_t slice = kXChunkBytes / rg.cs;
+          ptx::bulk_g2s_mc_hint(st + rg.rank * slice, x_img + (size_t)i * kXChunkBytes + rg.rank * slice, slice,
+                                &rg.full[rg.p_stage], (uint16_t)((1u << rg.cs) - 1u), rg.pol_x);
+        }
         ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
                            &rg.full[rg.p_stage], rg.pol_w);
         if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
@@ -284,7 +292,8 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
           }
           ws += n * kChunkK * 2 * 2;
         }
-        ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
+        if (rg.cs == 1) ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
+        else ptx::umma_commit_mc(&rg.empty[rg.c_stage], (uint16_t)((1u << rg.cs) - 1u));
         if (++rg.c_stage == kStages) { rg.c_stage = 0; rg.c_phase ^= 1; }
       }
       ptx::umma_commit(rg.acc);
@@ -313,7 +322,7 @@ struct KParams {
   float* q;                         // (64, 128) fp32
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   DecoderCtrl* ctrl;
-  int B, T, cap, infer, training, passes;
+  int B, T, cap, infer, training, passes, cluster;
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
 };
@@ -363,9 +372,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   uint8_t* s_weff = sp;                                                       // fused location filter image
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
+  rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
     ptx::mbar_init(rg.acc, 1);
     ptx::fence_barrier_init();
   }
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   ptx::fence_proxy_async();       // s_weff is read by tcgen05.mma (async proxy)
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync_all();   // peers' mbarriers are initialised before anyone multicasts
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -465,8 +476,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       T2_PROF(4);
     }
     // ======== attention for batch row `cta` ================================== model.py:43-86, 358-365
-    if (cta < p.B) {
-      const int b = cta;
+    if ((cta & 63) < p.B) {
+      // CTAs b and b+64 both evaluate row b's energies / softmax (no exchange needed, bit-identical);
+      // each produces one half of the context columns, the first writes the alignment row
+      const int b = cta & 63, ahalf = cta >> 6;
       for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
       for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
       // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], written as
@@ -523,24 +536,41 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         int nact = 0;
         for (int tl = 0; tl < ntiles; ++tl)
           if (tl * 128 + quad * 32 < T) nact = tl + 1;
+        // chunks of this warp: c = cg, cg+4, ... (8 accumulator columns each); processed-memory rows
+        // are prefetched 4 chunks at a time so their L2 latency overlaps
         float part = 0.f;
         int cur_tile = -1;
-        for (int c = cg; c < nact * 16; c += kWarps / 4) {
-          const int tile = c >> 4, col0 = (c & 15) * 8;
-          if (tile != cur_tile) {
-            if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
-            part = 0.f; cur_tile = tile;
-          }
-          const int j = tile * 128 + quad * 32 + lane;
-          float g[8];
-          ptx::tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + kColAtt + tile * 128 + col0, g);
-          if (j < T) {
-            const float* pmr = p.pm + ((long)b * T + j) * kAtt + col0;
-            const float4 p0 = __ldg(reinterpret_cast<const float4*>(pmr));
-            const float4 p1 = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-            const float pmv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
+          float4 pf[4][2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * (kWarps / 4);
+            const int j = (c >> 4) * 128 + quad * 32 + lane;
+            if (c < nact * 16 && j < T) {
+              const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
+              pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
+              pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+            } else {
+              pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * (kWarps / 4);
+            if (c >= nact * 16) break;
+            const int tile = c >> 4, col0 = (c & 15) * 8;
+            if (tile != cur_tile) {
+              if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+              part = 0.f; cur_tile = tile;
+            }
+            const int j = tile * 128 + quad * 32 + lane;
+            float g[8];
+            ptx::tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + kColAtt + tile * 128 + col0, g);
+            if (j < T) {
+              const float pmv[8] = {pf[u][0].x, pf[u][0].y, pf[u][0].z, pf[u][0].w, pf[u][1].x, pf[u][1].y, pf[u][1].z, pf[u][1].w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
+            }
           }
         }
         if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
@@ -575,27 +605,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         s_e[j] = a;
         s_pad0[halfk + j] = a;                                                // becomes "previous"
         s_pad1[halfk + j] += a;                                               // model.py:365
-        p.align[((long)b * p.cap + t) * T + j] = a;
+        if (ahalf == 0) p.align[((long)b * p.cap + t) * T + j] = a;
       }
       __syncthreads();
       {                                                           // context = aw . memory  model.py:83-84
-        float* scr = reinterpret_cast<float*>(rg.stage0);         // [4][512] partial sums (ring is idle)
-        const int c4 = tid & 127, jg = tid >> 7;
-        const float* mp = p.memory + (long)b * T * kEnc + c4 * 4;
+        float* scr = reinterpret_cast<float*>(rg.stage0);         // [8][256] partial sums (ring is idle)
+        const int c4 = tid & 63, jg = tid >> 6;                   // 64 float4 = this CTA's 256 columns; 8 j-groups
+        const float* mp = p.memory + (long)b * T * kEnc + ahalf * (kEnc / 2) + c4 * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int j = jg; j < T; j += 4) {
+#pragma unroll 10
+        for (int j = jg; j < T; j += 8) {
           const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (long)j * kEnc));
           const float a = s_e[j];
           acc.x = fmaf(a, m.x, acc.x); acc.y = fmaf(a, m.y, acc.y); acc.z = fmaf(a, m.z, acc.z); acc.w = fmaf(a, m.w, acc.w);
         }
-        *reinterpret_cast<float4*>(scr + jg * kEnc + c4 * 4) = acc;
+        *reinterpret_cast<float4*>(scr + jg * (kEnc / 2) + c4 * 4) = acc;
         __syncthreads();
-        if (tid < kEnc / 2) {
+        if (tid < kEnc / 4) {
           const int col = tid * 2;
-          const float v0 = (scr[col] + scr[kEnc + col]) + (scr[2 * kEnc + col] + scr[3 * kEnc + col]);
-          const float v1 = (scr[col + 1] + scr[kEnc + col + 1]) + (scr[2 * kEnc + col + 1] + scr[3 * kEnc + col + 1]);
-          store_split2(p.ctx_img, b, col, v0, v1);
+          float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { v0 += scr[g * (kEnc / 2) + col]; v1 += scr[g * (kEnc / 2) + col + 1]; }
+          store_split2(p.ctx_img, b, ahalf * (kEnc / 2) + col, v0, v1);
         }
       }
     }
@@ -742,6 +773,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     for (int b = tid; b < p.B; b += kThreads)
       if (!p.infer || !__ldcg(&ctrl->done[b])) p.mel_lengths[b] = ns;
     if (tid == 0) *p.n_steps = ns;
+  }
+  if (p.cluster > 1) {
+    // every stage this CTA filled has been released by all peers (their commits arrive on OUR
+    // barriers) before anyone leaves, then leave together
+    if (tid == 0)
+      for (int s = 0; s < kStages; ++s) {
+        mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 204);
+        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
+      }
+    __syncthreads();
+    ptx::cluster_sync_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -913,8 +955,35 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   }
   const size_t smem = persistent_smem_bytes(T);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = {(void*)&p};
-  T2_CUDA(cudaLaunchCooperativeKernel((void*)decoder_persistent_kernel, dim3(kG), dim3(kThreads), args, smem, s));
+  {
+    const char* e = getenv("T2_CLUSTER");      // 1 disables the TMA multicast of the activation stream
+    p.cluster = e ? atoi(e) : kCluster;
+    if (p.cluster != 1 && p.cluster != 2 && p.cluster != 4 && p.cluster != 8) p.cluster = kCluster;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; ++na;   // co-residency of all 128 CTAs
+  if (p.cluster > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = p.cluster; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1; ++na;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
+  if (le != cudaSuccess && p.cluster > 1) {
+    // some driver/runtime combinations reject cooperative + cluster launches: 128 CTAs at one CTA per
+    // SM are co-resident on a 148-SM part anyway (checked by occupancy below), so launch without the flag
+    (void)cudaGetLastError();
+    int max_clusters = 0;
+    cfg.attrs = attrs + 1; cfg.numAttrs = 1;
+    T2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, decoder_persistent_kernel, &cfg));
+    if (max_clusters * p.cluster < kG)
+      return fail(T2_ERR_UNSUPPORTED, "persistent decoder: only %d clusters of %d CTAs can be co-resident", max_clusters, p.cluster);
+    le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
+  }
+  if (le != cudaSuccess) return fail(T2_ERR_CUDA, "persistent decoder launch failed: %s", cudaGetErrorString(le));
   g_launch_count++;
   return T2_OK;
 }
@@ -936,6 +1005,7 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = rg.pol_w = ptx::policy_evict_last();
+  rg.cs = 1; rg.rank = 0;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);

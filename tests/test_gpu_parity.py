@@ -38,7 +38,7 @@ def test_native_library_is_loaded():
     assert info[1] == 10, "sm_100 device expected, got sm_%d%d" % (info[1], info[2])
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 5e-6), (1, 2e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 2e-5), (1, 2e-3)])
 @pytest.mark.parametrize("N,K", [(32, 256), (8, 64), (64, 1024), (72 - 8, 192)])
 def test_umma_split_gemm_selftest(N, K, passes, tol):
     """tcgen05 engine of the persistent decoder: C = 2 * A (64xK) . W (NxK)^T (two accumulating runs)."""
