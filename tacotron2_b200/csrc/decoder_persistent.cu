@@ -1,26 +1,33 @@
 // T2_IMPL_PERSISTENT: the whole autoregressive decoder loop (model.py:381-454) as ONE persistent
 // cooperative sm_100a kernel.
 //
-//   * 128 CTAs (one per SM), 512 threads each.  CTA c owns hidden units [8c, 8c+8) of BOTH LSTM
-//     cells (attention_rnn, decoder_rnn): their cell state lives in registers for the whole loop,
+//   * 128 CTAs (one per SM) in clusters, 512 threads each.  CTA c owns hidden units [8c, 8c+8) of BOTH
+//     LSTM cells (attention_rnn, decoder_rnn): their cell state lives in registers for the whole loop,
 //     their gate pre-activations accumulate in tensor memory (TMEM) across events.
-//   * "activation driven" schedule: whenever a new activation block (x2, ah, ctx, dh, x1) is
-//     complete, every CTA streams it ONCE through a shared-memory ring (bulk async copies, TMA
-//     engine) together with the slices of every weight matrix that consumes it and issues
-//     tcgen05.mma (M = 64 batch rows, N = 8..32 rows of W, fp32 accumulate in TMEM):
+//   * "activation driven" schedule: whenever a new activation block (x2, ah, ctx, dh, x1) is complete,
+//     every CTA streams it ONCE through a shared-memory ring (bulk async copies on the TMA engine; the
+//     activation chunk is multicast to the CTAs of a cluster) together with the slices of every weight
+//     matrix that consumes it, and ONE elected thread issues tcgen05.mma:
 //        x2_t  -> att gates += W_ih^a[:, :256] x2                          -> ah_t, ac_t
-//        ah_t  -> dec gates += W_ih^d[:, :1024] ah ; att gates(t+1) = W_hh^a ah ; q = W_q ah
+//        ah_t  -> dec gates += W_ih^d[:, :1024] ah ; att gates(t+1) += W_hh^a ah ; q = W_q ah
 //        ctx_t -> dec gates += W_ih^d[:, 1024:] ctx ; att gates(t+1) += W_ih^a[:, 256:] ctx ;
-//                 proj = W_P[:, 1024:] ctx                                  -> dh_t, dc_t
-//        dh_t  -> proj += W_P[:, :1024] dh ; dec gates(t+1) = W_hh^d dh    -> mel_t, gate_t, x1
+//                 proj += W_P[:, 1024:] ctx                                 -> dh_t, dc_t
+//        dh_t  -> proj += W_P[:, :1024] dh ; dec gates(t+1) += W_hh^d dh   -> mel_t, gate_t, x1
 //        x1    -> x2_(t+1) = relu(W_2 x1) * mask
 //     W_P stacks linear_projection, gate_layer and (W_1 . W_proj), so the first prenet layer of the
 //     NEXT step is computed from [dh; ctx] directly (model.py:97-100, 373-378, 449).
-//   * fp32-grade arithmetic on fp16 tensor cores: every operand is split x = hi + lo (two fp16), the
-//     product is hi*hi + lo*hi + hi*lo accumulated in fp32 (3 MMAs) -- DESIGN.md "precision".
-//   * location-sensitive attention (model.py:43-86) runs per batch row on CTA b with warp-shuffle
-//     reductions; previous / cumulative attention weights stay in shared memory across steps.
-//   * events are separated by a grid-wide barrier (global atomic counter + generation flag).
+//   * fp32-grade arithmetic on fp16 tensor cores: every operand is split x = hi + lo (two fp16).  The
+//     activation chunk image [hi rows 0-63 | lo rows 64-127] is ONE M=128 A operand; the weight rows of
+//     all consumers of an event are concatenated along N, once as hi and once as lo; two MMAs per
+//     16-wide K step give all four partial products (hi.hi, lo.hi, hi.lo, lo.lo) in fp32:
+//        D_hi[128 x N] += [X_hi; X_lo] . W_hi^T      D_lo[128 x N] += [X_hi; X_lo] . W_lo^T
+//     gates[r] = D_hi[r] + D_lo[r] + D_hi[64+r] + D_lo[64+r]  (summed in the epilogue).
+//     Accumulators are always accumulated into and zeroed by the epilogue that consumed them.
+//   * location-sensitive attention (model.py:43-86): location conv + dense are fused into one 62-tap
+//     filter bank evaluated as a tensor-core GEMM over an im2col image of the previous / cumulative
+//     weights (kept in shared memory across steps); energies, softmax and context per batch row on a
+//     CTA pair with warp-shuffle reductions.
+//   * events are separated by a grid-wide barrier (monotonic global counter, red.release / ld.acquire).
 #include <stdlib.h>
 #include <string.h>
 
@@ -38,27 +45,28 @@ constexpr int kG = 128;               // CTAs
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
-constexpr int kCluster = 8;            // CTAs per cluster: activation chunks are TMA-multicast to all of them
-constexpr int kRows = 64;             // MMA M (batch rows, zero padded)
-constexpr int kXChunkBytes = kRows * kChunkK * 2 * 2;   // hi + lo planes = 16 KiB
-constexpr int kWStageMax = 72 * kChunkK * 2 * 2;        // up to 72 W rows per stage = 18 KiB
-constexpr int kStageBytes = kXChunkBytes + kWStageMax;
+constexpr int kRows = 64;             // batch rows per launch (zero padded)
+constexpr int kXChunkBytes = 2 * kRows * kChunkK * 2;    // [hi 64 rows | lo 64 rows] x 64 k fp16 = 16 KiB
+constexpr int kColA = 0, kColD = 32, kColS = 64;         // hi-part accumulator columns: att | dec | shared slot
+constexpr int kHiCols = 80;                               // lo-part accumulators live at +kHiCols
+constexpr int kColAtt = 160;                              // attention pa accumulators: 2 tiles x 128 columns
 constexpr int kTmemCols = 512;
-constexpr int kColA = 0, kColD = 32, kColP = 64, kColQ = 72, kColX2 = 80;
-constexpr int kColAtt = 128;          // attention pa accumulators: up to 3 tiles of 128 rows x 128 columns
-constexpr int kMaxAttTiles = 3;       // T_enc <= 384
-constexpr int kWeffBytes = kAtt * kChunkK * 2 * 2;   // fused location filter image (hi+lo) = 32 KiB
+constexpr int kWStageMax = 2 * kHiCols * kChunkK * 2;    // hi + lo planes of up to 80 weight rows = 20 KiB
+constexpr int kStageBytes = kXChunkBytes + kWStageMax;   // 36 KiB
 constexpr int kNumEvents = 5;         // x2, ah, ctx, dh, x1
 constexpr int kPCols = 344;           // 80 mel + 1 gate + 256 x1 + 7 pad
 constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 43;
+constexpr int kWeffBytes = kAtt * kChunkK * 2 * 2;        // fused location filter image (hi+lo) = 32 KiB
+constexpr int kXchStride = 33;
 constexpr unsigned long long kWatchdogCycles = 1ull << 32;   // ~2 s
 
 struct EventPlan {
   uint32_t w_off;       // byte offset of this CTA's first chunk in the W image buffer
-  uint32_t w_bytes;     // W bytes per chunk (sum over consumers of n*256)
+  uint32_t w_bytes;     // W bytes per chunk = 2 planes x nrows x 128
+  int32_t nrows;        // weight rows of all consumers (MMA N); 0 = this CTA skips the event
+  int32_t col0;         // hi-part accumulator column of the first consumer
   int32_t ncons;
-  int32_t n[3];         // rows of W (MMA N) per consumer
-  int32_t col[3];       // TMEM accumulator column per consumer
+  int32_t n[3];         // rows per consumer (packing only)
 };
 struct CtaPlan {
   EventPlan ev[kNumEvents];
@@ -71,7 +79,7 @@ struct PersistentPack {
   float* bias_p = nullptr;            // (344): proj bias | gate bias | W1.b_proj | 0
   float* bias_a = nullptr;            // (kG, 32) att LSTM bias in TMEM column order
   float* bias_d = nullptr;            // (kG, 32)
-  int32_t* rows = nullptr;            // scratch row tables for packing
+  int32_t* rows = nullptr;            // row tables for packing
   float* weff = nullptr;              // (128, 64) fp32 fused location filter W_ld . W_loc (62 taps + 2 zero)
   uint8_t* weff_img = nullptr;        // its split-fp16 operand image (32 KiB)
 };
@@ -123,8 +131,9 @@ __global__ void pack_rows_image_kernel(const float* __restrict__ W, int N, int K
   }
 }
 
-// one consumer of one event: for CTA blockIdx.y, chunk blockIdx.x: write [hi plane | lo plane] of the
-// n rows rows_tab[cta*32 + i] (-1 = zero row) x 64 columns starting at kcol0 + chunk*64.
+// one consumer of one event: for CTA blockIdx.y, chunk blockIdx.x: rows rows_tab[cta*32 + i] (-1 = zero
+// row) x 64 columns starting at kcol0 + chunk*64 go to rows [roff, roff+n) of the chunk's hi and lo planes
+// (each plane holds the rows of ALL consumers of the event, concatenated).
 __global__ void pack_consumer_kernel(const float* __restrict__ src, int ld, int kcol0,
                                      const int32_t* __restrict__ rows_tab, const CtaPlan* __restrict__ plans,
                                      int ev, int cons, uint8_t* __restrict__ wimg) {
@@ -132,17 +141,17 @@ __global__ void pack_consumer_kernel(const float* __restrict__ src, int ld, int 
   const EventPlan& ep = plans[cta].ev[ev];
   if (cons >= ep.ncons) return;
   const int n = ep.n[cons];
-  uint32_t off = ep.w_off + (uint32_t)chunk * ep.w_bytes;
-  for (int i = 0; i < cons; ++i) off += ep.n[i] * 256;
-  __half* hi = reinterpret_cast<__half*>(wimg + off);
-  __half* lo = hi + n * 64;
+  int roff = 0;
+  for (int i = 0; i < cons; ++i) roff += ep.n[i];
+  __half* hi = reinterpret_cast<__half*>(wimg + ep.w_off + (size_t)chunk * ep.w_bytes);
+  __half* lo = hi + ep.nrows * 64;
   for (int i = threadIdx.x; i < n * 64; i += blockDim.x) {
     const int r = i >> 6, k = i & 63;
     const int srow = rows_tab[cta * 32 + r];
     const float v = srow >= 0 ? src[(long)srow * ld + kcol0 + chunk * 64 + k] : 0.f;
     __half h, l;
     split_fp16(v, h, l);
-    const uint32_t e = img_elem_offset(r, k);
+    const uint32_t e = img_elem_offset(roff + r, k);
     hi[e] = h; lo[e] = l;
   }
 }
@@ -154,7 +163,7 @@ __global__ void pack_lstm_bias_kernel(const float* __restrict__ b_sum, float* __
   out[i] = b_sum[g * 1024 + cta * 8 + ul];
 }
 
-// fp32 rows (n_rows x K, ld) -> operand images (chunks x [hi|lo] planes of 64 x 64), rows >= n_rows zero
+// fp32 rows (n_rows x K, ld) -> activation images: chunks x [hi rows 0-63 | lo rows 64-127] x 64 k
 __global__ void rows_to_image_kernel(const float* __restrict__ src, long ld, int n_rows, int K,
                                      long src_block_stride, uint8_t* __restrict__ dst, long dst_block_stride) {
   const float* s = src + (long)blockIdx.y * src_block_stride;
@@ -239,13 +248,14 @@ struct Ring {
   uint32_t cs, rank;           // cluster size (1 = no multicast) and this CTA's rank in it
 };
 
-// Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight slices through the
-// ring and issues the MMAs.  Called by all threads; returns after the accumulators are complete.
+// Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight rows through the ring
+// and issues the MMAs (2 per 16-wide K step).  Called by all threads; returns after the accumulators are
+// complete.  Every MMA accumulates (the epilogues zero what they consume).
 __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
-                                          const uint8_t* w_img, int chunks, uint32_t fresh_mask,
-                                          int passes, uint32_t tmem_base, DecoderCtrl* ctrl) {
+                                          const uint8_t* w_img, int chunks, uint32_t tmem_base,
+                                          DecoderCtrl* ctrl) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (ep.ncons == 0) return;           // this CTA has no consumer of this activation
+  if (ep.nrows == 0) return;           // this CTA (and its whole cluster) has no consumer of this activation
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < chunks; ++i) {
@@ -267,30 +277,21 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
+      const uint32_t n = (uint32_t)ep.nrows;
+      const uint32_t idesc = ptx::make_idesc_f16(128, n);
+      const uint32_t d_hi = tmem_base + (uint32_t)ep.col0, d_lo = d_hi + kHiCols;
       for (int i = 0; i < chunks; ++i) {
         mbar_wait(&rg.full[rg.c_stage], rg.c_phase, ctrl, 201);
         ptx::tc_fence_after();
         const uint32_t xs = ptx::smem_u32(rg.stage(rg.c_stage));
-        uint32_t ws = xs + kXChunkBytes;
-        for (int c = 0; c < ep.ncons; ++c) {
-          const uint32_t n = (uint32_t)ep.n[c];
-          const uint32_t idesc = ptx::make_idesc_f16_m64(n);
-          const uint32_t d = tmem_base + (uint32_t)ep.col[c];
-          const bool fresh = (fresh_mask >> c) & 1u;
+        const uint32_t ws = xs + kXChunkBytes;
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / 16; ++kk) {
-            const uint64_t a_hi = ptx::make_smem_desc(xs + kk * 256, 128, 1024);
-            const uint64_t a_lo = ptx::make_smem_desc(xs + kRows * kChunkK * 2 + kk * 256, 128, 1024);
-            const uint64_t b_hi = ptx::make_smem_desc(ws + kk * 256, 128, 1024);
-            const uint64_t b_lo = ptx::make_smem_desc(ws + n * kChunkK * 2 + kk * 256, 128, 1024);
-            const uint32_t acc0 = (fresh && i == 0 && kk == 0) ? 0u : 1u;
-            ptx::umma_f16(d, a_hi, b_hi, idesc, acc0);
-            if (passes == 3) {
-              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
-              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
-            }
-          }
-          ws += n * kChunkK * 2 * 2;
+        for (int kk = 0; kk < kChunkK / 16; ++kk) {
+          const uint64_t a = ptx::make_smem_desc(xs + kk * 256, 128, 1024);              // [X_hi ; X_lo], M = 128
+          const uint64_t b_hi = ptx::make_smem_desc(ws + kk * 256, 128, 1024);
+          const uint64_t b_lo = ptx::make_smem_desc(ws + n * kChunkK * 2 + kk * 256, 128, 1024);
+          ptx::umma_f16(d_hi, a, b_hi, idesc, 1u);
+          ptx::umma_f16(d_lo, a, b_lo, idesc, 1u);
         }
         if (rg.cs == 1) ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
         else ptx::umma_commit_mc(&rg.empty[rg.c_stage], (uint16_t)((1u << rg.cs) - 1u));
@@ -305,12 +306,22 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
   ptx::tc_fence_after();
 }
 
+// this lane's 8 accumulator columns: hi-part + lo-part, then zero both (they are consumed)
+__device__ __forceinline__ void acc_take8(uint32_t t_lane, int col, float* s) {
+  float a[8], b[8];
+  ptx::tmem_ld8(t_lane + col, a);
+  ptx::tmem_ld8(t_lane + kHiCols + col, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = a[i] + b[i];
+  ptx::tmem_zero8(t_lane + col);
+  ptx::tmem_zero8(t_lane + kHiCols + col);
+  ptx::tmem_wait_st();
+}
+
 struct KParams {
-  const PersistentPack* pk_unused;
   const CtaPlan* plans;
   const uint8_t* wimg;
   const float* bias_a; const float* bias_d; const float* bias_p;
-  // attention weights (fp32, caller's tensors)
   const uint8_t* weff_img; const float* w_v;
   float l2_pin_frac;
   // tensors
@@ -322,7 +333,7 @@ struct KParams {
   float* q;                         // (64, 128) fp32
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   DecoderCtrl* ctrl;
-  int B, T, cap, infer, training, passes, cluster;
+  int B, T, cap, infer, training, cluster;
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
 };
@@ -330,16 +341,14 @@ struct KParams {
 __device__ __forceinline__ void store_split2(uint8_t* img, int row, int k, float v0, float v1) {
   // two adjacent K elements (k even) of an activation image: 4-byte stores into the hi and lo planes
   const int chunk = k >> 6, kc = k & 63;
-  __half2 h, l;
   __half h0, l0, h1, l1;
   split_fp16(v0, h0, l0);
   split_fp16(v1, h1, l1);
-  h = __halves2half2(h0, h1); l = __halves2half2(l0, l1);
   __half* hi = reinterpret_cast<__half*>(img + (size_t)chunk * kXChunkBytes);
   __half* lo = hi + kRows * kChunkK;
   const uint32_t e = img_elem_offset(row, kc);
-  *reinterpret_cast<__half2*>(hi + e) = h;
-  *reinterpret_cast<__half2*>(lo + e) = l;
+  *reinterpret_cast<__half2*>(hi + e) = __halves2half2(h0, h1);
+  *reinterpret_cast<__half2*>(lo + e) = __halves2half2(l0, l1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,11 +359,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
   const int T = p.T, TP = T + kLocK - 1;
+  const int ntiles = (T + 127) >> 7;
 
   // ---- shared memory carve-up ----
   uint8_t* sp = smem_raw;
   Ring rg;
   rg.stage0 = sp; sp += kStages * kStageBytes;
+  uint8_t* s_weff = sp; sp += kWeffBytes;                                     // fused location filter image
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
   rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
@@ -364,12 +375,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   float* s_v = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_q = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
+  float* s_xch = reinterpret_cast<float*>(sp); sp += kRows * kXchStride * 4;  // lo-row halves of the accumulators
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
-  const int ntiles = (T + 127) >> 7;
-  float* s_e = reinterpret_cast<float*>(sp); sp += ntiles * 128 * 4;
-  sp = smem_raw + (((sp - smem_raw) + 1023) & ~(size_t)1023);
-  uint8_t* s_weff = sp;                                                       // fused location filter image
+  float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128]
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
@@ -400,18 +409,25 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 
   const CtaPlan& plan = p.plans[cta];
   DecoderCtrl* ctrl = p.ctrl;
-  unsigned int bar_gen = 0;
-  // epilogue role of this thread: TMEM lane quadrant q = warp % 4 (hardware rule), column group
-  // cg = warp / 4; valid rows are lanes 0..15 of each quadrant for M = 64 accumulators.
+  unsigned int bar_target = 0;
+  // epilogue role of this thread: TMEM lane quadrant quad = warp % 4 (hardware rule), column group
+  // cg = warp / 4.  Accumulator lane = MMA row: lanes 0-63 are the X_hi rows (batch rows), lanes 64-127
+  // the X_lo rows of the same batch rows; quadrants 2/3 hand their partial sums to quadrants 0/1.
   const int quad = warp & 3, cg = warp >> 2;
-  const int row = quad * 16 + lane;                   // batch row of this thread (lane < 16)
-  const bool erow = lane < 16 && row < p.B;
+  const int row = (quad & 1) * 32 + lane;               // batch row of this lane
+  const bool is_lo = quad >= 2;
+  const bool erow = !is_lo && row < p.B;
   const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
   float c_att[2] = {0.f, 0.f}, c_dec[2] = {0.f, 0.f};  // cell states of units 8*cta + 2*cg + {0,1}
   const bool has_q = cta >= kQCta0 && cta < kQCta0 + kQCtas;
   const bool has_x2 = cta >= kX2Cta0 && cta < kX2Cta0 + kX2Ctas;
   const bool has_p = cta >= kPCta0 && cta < kPCta0 + kPCtas;
   const int halfk = (kLocK - 1) / 2;
+  // zero the LSTM / shared-slot accumulators once (every MMA accumulates)
+  for (int c = cg * 40; c < cg * 40 + 40; c += 8) ptx::tmem_zero8(t_lane + c);
+  ptx::tmem_wait_st();
+  ptx::tc_fence_before();
+  __syncthreads();
   // phase profile (cycles, accumulated over steps) on three sample CTAs; see t2_decoder_profile()
   const int prof_slot = cta == 0 ? 0 : (cta == 60 ? 1 : (cta == 100 ? 2 : -1));
   long long prof_last = clock64();
@@ -423,15 +439,30 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       prof_last = now_;                                                    \
     }                                                                      \
   } while (0)
+  // LSTM epilogue shared by both cells: take the 8 gate columns (2 units x i,f,g,o) of this lane,
+  // combine hi-row and lo-row partial sums through shared memory, return them in g[] for batch rows
+#define T2_TAKE_GATES(colbase, g)                                                        \
+  do {                                                                                   \
+    acc_take8(t_lane, (colbase) + cg * 8, g);                                            \
+    if (is_lo) {                                                                         \
+      _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) s_xch[row * kXchStride + cg * 8 + i_] = g[i_]; \
+    }                                                                                    \
+    ptx::tc_fence_before();                                                              \
+    __syncthreads();                                                                     \
+    if (!is_lo) {                                                                        \
+      _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) g[i_] += s_xch[row * kXchStride + cg * 8 + i_]; \
+    }                                                                                    \
+  } while (0)
+
   int t = 0;
   for (; t < p.cap; ++t) {
     // ======== E0: x2_t -> attention LSTM gates, epilogue -> ah_t ==================== model.py:352-356
     {
       const uint8_t* x2 = p.infer ? p.x2_img : p.teacher_x2_img + (size_t)t * 4 * kXChunkBytes;
-      run_event(rg, plan.ev[0], x2, p.wimg, 4, t == 0 ? 1u : 0u, p.passes, tmem_base, ctrl);
+      run_event(rg, plan.ev[0], x2, p.wimg, 4, tmem_base, ctrl);
       T2_PROF(0);
       float g[8];
-      ptx::tmem_ld8(t_lane + kColA + cg * 8, g);
+      T2_TAKE_GATES(kColA, g);
       if (erow) {
         float hv[2];
 #pragma unroll
@@ -454,129 +485,136 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
-      ptx::tc_fence_before();
       T2_PROF(1);
-      grid_barrier(ctrl, bar_gen);                                             // B1: ah_t complete
+      grid_barrier(ctrl, bar_target);                                          // B1: ah_t complete
       T2_PROF(2);
     }
     // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
     {
-      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, (t == 0 ? 1u : 0u) | 2u | 4u, p.passes, tmem_base, ctrl);
-      if (has_q && cg == 0) {
+      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl);
+      if (has_q) {
         float g[8];
-        ptx::tmem_ld8(t_lane + kColQ, g);
-        if (erow) {
+        if (cg == 0) acc_take8(t_lane, kColS, g);
+        if (cg == 0 && is_lo) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) p.q[row * kAtt + (cta - kQCta0) * 8 + j] = g[j];
+          for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (cg == 0 && erow) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p.q[row * kAtt + (cta - kQCta0) * 8 + j] = g[j] + s_xch[row * kXchStride + j];
         }
       }
-      ptx::tc_fence_before();
       T2_PROF(3);
-      grid_barrier(ctrl, bar_gen);                                             // B2: q complete
+      grid_barrier(ctrl, bar_target);                                          // B2: q complete
       T2_PROF(4);
     }
-    // ======== attention for batch row `cta` ================================== model.py:43-86, 358-365
+    // ======== attention for batch row (cta mod 64) ============================ model.py:43-86, 358-365
     if ((cta & 63) < p.B) {
       // CTAs b and b+64 both evaluate row b's energies / softmax (no exchange needed, bit-identical);
       // each produces one half of the context columns, the first writes the alignment row
       const int b = cta & 63, ahalf = cta >> 6;
       for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
       for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
-      // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], written as
-      //     split-fp16 canonical tiles of 128 rows into the (idle) operand ring           model.py:23
       uint8_t* aimg = rg.stage0;
-      for (int item = tid; item < ntiles * 128 * 8; item += kThreads) {
-        const int j = item >> 3, g8 = item & 7;
-        const int tile = j >> 7, r = j & 127;
-        __align__(16) __half hh[8];
-        __align__(16) __half ll[8];
+      for (int t0 = 0; t0 < ntiles; t0 += 2) {            // rounds of up to 2 tiles of 128 positions
+        const int nt = min(2, ntiles - t0);
+        const int j_end = min(T, (t0 + nt) * 128);
+        // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
+        //     canonical tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
+        //     accumulator rows are never read                                        model.py:23
+        for (int item = t0 * 128 * 8 + tid; item < j_end * 8; item += kThreads) {
+          const int j = item >> 3, g8 = item & 7;
+          const int tile = (j >> 7) - t0, r = j & 127;
+          __align__(16) __half hh[8];
+          __align__(16) __half ll[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int kk = g8 * 8 + e;
-          float v = 0.f;
-          if (kk < 2 * kLocK && j < T) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
-          split_fp16(v, hh[e], ll[e]);
+          for (int e = 0; e < 8; ++e) {
+            const int kk = g8 * 8 + e;
+            float v = 0.f;
+            if (kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
+            split_fp16(v, hh[e], ll[e]);
+          }
+          uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + g8 * 128 + (r & 7) * 16;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
+          *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
         }
-        uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + g8 * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
-      }
-      ptx::fence_proxy_async();
-      __syncthreads();
-      // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
-      //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
-      if (warp == 1) {
-        if (lane == 0) {
-          ptx::tc_fence_after();
-          const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
-          const uint32_t idesc = ptx::make_idesc_f16(128, 128);
-          for (int tile = 0; tile < ntiles; ++tile) {
-            const uint32_t d = tmem_base + kColAtt + tile * 128;
+        ptx::fence_proxy_async();
+        __syncthreads();
+        // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
+        //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
+        if (warp == 1) {
+          if (lane == 0) {
+            ptx::tc_fence_after();
+            const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
+            const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+            for (int tile = 0; tile < nt; ++tile) {
+              const uint32_t d = tmem_base + kColAtt + tile * 128;
 #pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
-              const uint64_t a_hi = ptx::make_smem_desc(as + tile * 32768 + kk * 256, 128, 1024);
-              const uint64_t a_lo = ptx::make_smem_desc(as + tile * 32768 + 16384 + kk * 256, 128, 1024);
-              const uint64_t b_hi = ptx::make_smem_desc(bs + kk * 256, 128, 1024);
-              const uint64_t b_lo = ptx::make_smem_desc(bs + 16384 + kk * 256, 128, 1024);
-              ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
-              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
-              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                const uint64_t a_hi = ptx::make_smem_desc(as + tile * 32768 + kk * 256, 128, 1024);
+                const uint64_t a_lo = ptx::make_smem_desc(as + tile * 32768 + 16384 + kk * 256, 128, 1024);
+                const uint64_t b_hi = ptx::make_smem_desc(bs + kk * 256, 128, 1024);
+                const uint64_t b_lo = ptx::make_smem_desc(bs + 16384 + kk * 256, 128, 1024);
+                ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
+                ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+                ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+              }
+            }
+            ptx::umma_commit(rg.acc);
+          }
+          __syncwarp();
+        }
+        mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
+        rg.acc_phase ^= 1;
+        ptx::tc_fence_after();
+        // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
+        //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
+        {
+          int nact = 0;
+          for (int tl = 0; tl < nt; ++tl)
+            if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
+          float part = 0.f;
+          int cur_tile = -1;
+          for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
+            float4 pf[4][2];      // processed-memory rows, prefetched 4 chunks at a time
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = c0 + u * (kWarps / 4);
+              const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
+              if (c < nact * 16 && j < T) {
+                const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
+                pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
+                pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+              } else {
+                pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = c0 + u * (kWarps / 4);
+              if (c >= nact * 16) break;
+              const int tile = c >> 4, col0 = (c & 15) * 8;
+              if (tile != cur_tile) {
+                if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+                part = 0.f; cur_tile = tile;
+              }
+              const int j = (t0 + tile) * 128 + quad * 32 + lane;
+              float g[8];
+              ptx::tmem_ld8(t_lane + kColAtt + tile * 128 + col0, g);
+              if (j < T) {
+                const float pmv[8] = {pf[u][0].x, pf[u][0].y, pf[u][0].z, pf[u][0].w, pf[u][1].x, pf[u][1].y, pf[u][1].z, pf[u][1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
+              }
             }
           }
-          ptx::umma_commit(rg.acc);
+          if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
         }
-        __syncwarp();
+        ptx::tc_fence_before();
+        __syncthreads();
       }
-      mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
-      rg.acc_phase ^= 1;
-      ptx::tc_fence_after();
-      // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
-      //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
-      {
-        int nact = 0;
-        for (int tl = 0; tl < ntiles; ++tl)
-          if (tl * 128 + quad * 32 < T) nact = tl + 1;
-        // chunks of this warp: c = cg, cg+4, ... (8 accumulator columns each); processed-memory rows
-        // are prefetched 4 chunks at a time so their L2 latency overlaps
-        float part = 0.f;
-        int cur_tile = -1;
-        for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
-          float4 pf[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * (kWarps / 4);
-            const int j = (c >> 4) * 128 + quad * 32 + lane;
-            if (c < nact * 16 && j < T) {
-              const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
-              pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
-              pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-            } else {
-              pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * (kWarps / 4);
-            if (c >= nact * 16) break;
-            const int tile = c >> 4, col0 = (c & 15) * 8;
-            if (tile != cur_tile) {
-              if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
-              part = 0.f; cur_tile = tile;
-            }
-            const int j = tile * 128 + quad * 32 + lane;
-            float g[8];
-            ptx::tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + kColAtt + tile * 128 + col0, g);
-            if (j < T) {
-              const float pmv[8] = {pf[u][0].x, pf[u][0].y, pf[u][0].z, pf[u][0].w, pf[u][1].x, pf[u][1].y, pf[u][1].z, pf[u][1].w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
-            }
-          }
-        }
-        if (cur_tile >= 0) { const int jp = cur_tile * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
-      }
-      ptx::tc_fence_before();
-      __syncthreads();
       const int len = p.mem_len ? p.mem_len[b] : T;
       float mx = -INFINITY;                                     // mask + softmax         model.py:79-82
       for (int j = tid; j < T; j += kThreads) {
@@ -631,14 +669,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       }
     }
     T2_PROF(5);
-    grid_barrier(ctrl, bar_gen);                                               // B3: ctx_t complete
+    grid_barrier(ctrl, bar_target);                                            // B3: ctx_t complete
     T2_PROF(6);
     // ======== E2: ctx_t -> dec gates (rest), next att gates, projection (part); epilogue -> dh_t
     {
-      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, 4u, p.passes, tmem_base, ctrl);
+      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, tmem_base, ctrl);
       T2_PROF(7);
       float g[8];
-      ptx::tmem_ld8(t_lane + kColD + cg * 8, g);
+      T2_TAKE_GATES(kColD, g);
       if (erow) {
         float hv[2];
 #pragma unroll
@@ -661,66 +699,56 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         store_split2(p.dh_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
-      ptx::tc_fence_before();
       T2_PROF(8);
-      grid_barrier(ctrl, bar_gen);                                             // B4: dh_t complete
+      grid_barrier(ctrl, bar_target);                                          // B4: dh_t complete
       T2_PROF(9);
     }
     // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
     {
-      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, 1u, p.passes, tmem_base, ctrl);
+      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl);
       T2_PROF(10);
       if (tid == 0) *s_live = 0;
+      float g[8];
+      if (has_p && cg == 0) acc_take8(t_lane, kColS, g);
+      if (has_p && cg == 0 && is_lo) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+      }
+      ptx::tc_fence_before();
       __syncthreads();
-      if (has_p && cg == 0) {
-        float g[8];
-        ptx::tmem_ld8(t_lane + kColP, g);
-        if (erow) {
-          const int pc0 = (cta - kPCta0) * 8;
-          float x1v[8];
+      if (has_p && cg == 0 && erow) {
+        const int pc0 = (cta - kPCta0) * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int pc = pc0 + j;
-            const float v = g[j] + p.bias_p[pc];
-            x1v[j] = 0.f;
-            if (pc < kMel) {
-              p.mel[((long)row * p.cap + t) * kMel + pc] = v;                  // model.py:375-376
-            } else if (pc == kMel) {
-              p.gate[(long)row * p.cap + t] = v;                               // model.py:378
-              if (p.infer) {
-                int done = ctrl->done[row];
-                if (!done && sigmoid_exact(v) > p.gate_threshold) {           // model.py:443
-                  done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
-                }
-                if (!done) atomicAdd(s_live, 1);
+        for (int j = 0; j < 8; ++j) {
+          const int pc = pc0 + j;
+          const float v = g[j] + s_xch[row * kXchStride + j] + p.bias_p[pc];
+          if (pc < kMel) {
+            p.mel[((long)row * p.cap + t) * kMel + pc] = v;                    // model.py:375-376
+          } else if (pc == kMel) {
+            p.gate[(long)row * p.cap + t] = v;                                 // model.py:378
+            if (p.infer) {
+              int done = ctrl->done[row];
+              if (!done && sigmoid_exact(v) > p.gate_threshold) {             // model.py:443
+                done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
               }
-            } else if (pc < kMel + 1 + kPre) {                                 // first prenet layer of step t+1
-              const int col = pc - (kMel + 1);
-              float r = fmaxf(v, 0.f);
-              if (p.infer && t + 1 < p.cap) {
-                const long idx = (long)row * kPre + col;
-                const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
-                                                : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
-                r = keep ? r * 2.f : 0.f;
-              }
-              x1v[j] = r;
+              if (!done) atomicAdd(s_live, 1);
             }
-          }
-          if (p.infer) {
-            // columns pc0..pc0+7 that are x1 columns: col = pc - 81; pairs may straddle the mel/gate
-            // boundary only in CTA 10 (pc0 = 80): handle element-wise there.
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int pc = pc0 + j;
-              if (pc > kMel && pc < kMel + 1 + kPre) {
-                const int col = pc - (kMel + 1);
-                __half h, l;
-                split_fp16(x1v[j], h, l);
-                __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
-                __half* lo = hi + kRows * kChunkK;
-                const uint32_t e = img_elem_offset(row, col & 63);
-                hi[e] = h; lo[e] = l;
-              }
+          } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
+            const int col = pc - (kMel + 1);
+            float r = fmaxf(v, 0.f);
+            if (p.infer && t + 1 < p.cap) {
+              const long idx = (long)row * kPre + col;
+              const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
+                                              : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
+              r = keep ? r * 2.f : 0.f;
+            }
+            if (p.infer) {
+              __half h, l;
+              split_fp16(r, h, l);
+              __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
+              __half* lo = hi + kRows * kChunkK;
+              const uint32_t e = img_elem_offset(row, col & 63);
+              hi[e] = h; lo[e] = l;
             }
           }
         }
@@ -731,10 +759,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (p.infer && *s_live == 0) ctrl->all_done = 1;
         __threadfence();
       }
-      ptx::tc_fence_before();
       T2_PROF(11);
       if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
-      grid_barrier(ctrl, bar_gen);                                             // B5: x1 / stop flag complete
+      grid_barrier(ctrl, bar_target);                                          // B5: x1 / stop flag complete
       T2_PROF(12);
       int all_done;
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
@@ -742,11 +769,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     }
     // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
     {
-      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, 1u, p.passes, tmem_base, ctrl);
-      if (has_x2 && cg == 0) {
+      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl);
+      if (has_x2) {
         float g[8];
-        ptx::tmem_ld8(t_lane + kColX2, g);
-        if (erow) {
+        if (cg == 0) acc_take8(t_lane, kColS, g);
+        if (cg == 0 && is_lo) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (cg == 0 && erow) {
           const int col0 = (cta - kX2Cta0) * 8;
           float r[8];
 #pragma unroll
@@ -754,15 +787,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
             const long idx = (long)row * kPre + col0 + j;
             const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 1) * p.B * kPre + idx] != 0
                                             : philox_keep(p.seed, (t + 1) * 4 + 1, idx, 0.5f);
-            r[j] = keep ? fmaxf(g[j], 0.f) * 2.f : 0.f;
+            r[j] = keep ? fmaxf(g[j] + s_xch[row * kXchStride + j], 0.f) * 2.f : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 8; j += 2) store_split2(p.x2_img, row, col0 + j, r[j], r[j + 1]);
         }
       }
-      ptx::tc_fence_before();
       T2_PROF(13);
-      grid_barrier(ctrl, bar_gen);                                             // B6: x2_(t+1) complete
+      grid_barrier(ctrl, bar_target);                                          // B6: x2_(t+1) complete
       T2_PROF(14);
     }
   }
@@ -798,10 +830,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
-  size_t n = (size_t)kStages * kStageBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
-             2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4;
-  n = (n + 1023) & ~(size_t)1023;
-  return n + kWeffBytes + 1024;
+  return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
+         (size_t)kRows * kXchStride * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
 }
 
 size_t persistent_ws_bytes(int B, int T) {
@@ -815,7 +845,6 @@ bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
   if (m->sm_count < kG) return false;
   if (a->B > kRows) return false;
   if (a->mode != T2_MODE_INFER) return false;   // teacher forcing runs on the stepwise path for now
-  if (a->T_enc > 128 * kMaxAttTiles) return false;   // TMEM: 128 + 3 x 128 accumulator columns
   if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
   return true;
 }
@@ -824,7 +853,7 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
   PersistentPack* pk = (PersistentPack*)m->pk;
   if (!pk) { pk = new PersistentPack(); m->pk = pk; }
   const int kdc = kDRnn + kEnc;
-  // ---- per-CTA plans (host) ----
+  // ---- per-CTA plans (host).  Consumers of an event are a contiguous run of [A | D | S] ----
   std::vector<CtaPlan> plans(kG);
   size_t off = 0;
   for (int c = 0; c < kG; ++c) {
@@ -832,18 +861,19 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
                hp = c >= kPCta0 && c < kPCta0 + kPCtas;
     CtaPlan& pl = plans[c];
     memset(&pl, 0, sizeof(pl));
-    auto set = [&](int ev, int chunks, std::initializer_list<std::pair<int, int>> cons) {
+    auto set = [&](int ev, int chunks, int col0, std::initializer_list<int> ns) {
       EventPlan& e = pl.ev[ev];
-      e.ncons = 0; e.w_bytes = 0;
-      for (auto& pr : cons) { e.n[e.ncons] = pr.first; e.col[e.ncons] = pr.second; e.w_bytes += pr.first * 256; e.ncons++; }
+      e.ncons = 0; e.nrows = 0; e.col0 = col0;
+      for (int n : ns) { e.n[e.ncons++] = n; e.nrows += n; }
+      e.w_bytes = (uint32_t)e.nrows * 256;
       e.w_off = (uint32_t)off;
       off += (size_t)chunks * e.w_bytes;
     };
-    set(0, 4, {{32, kColA}});
-    if (hq) set(1, 16, {{32, kColD}, {32, kColA}, {8, kColQ}}); else set(1, 16, {{32, kColD}, {32, kColA}});
-    if (hp) set(2, 8, {{32, kColD}, {32, kColA}, {8, kColP}}); else set(2, 8, {{32, kColD}, {32, kColA}});
-    if (hp) set(3, 16, {{32, kColD}, {8, kColP}}); else set(3, 16, {{32, kColD}});
-    if (hx) set(4, 4, {{8, kColX2}}); else { pl.ev[4].ncons = 0; pl.ev[4].w_bytes = 0; pl.ev[4].w_off = (uint32_t)off; }
+    set(0, 4, kColA, {32});
+    if (hq) set(1, 16, kColA, {32, 32, 16}); else set(1, 16, kColA, {32, 32});
+    if (hp) set(2, 8, kColA, {32, 32, 16}); else set(2, 8, kColA, {32, 32});
+    if (hp) set(3, 16, kColD, {32, 16}); else set(3, 16, kColD, {32});
+    if (hx) set(4, 4, kColS, {16}); else { pl.ev[4].w_off = (uint32_t)off; }
   }
   if (off >= (size_t)4 << 30) return fail(T2_ERR_INVALID, "W image too large");
   if (!pk->wimg) {
@@ -876,7 +906,7 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
   T2_LAUNCH_CHECK();
   pack_lstm_bias_kernel<<<(kG * 32 + 255) / 256, 256, 0, s>>>(m->drnn_b, pk->bias_d);
   T2_LAUNCH_CHECK();
-  // ---- row tables: [0] LSTM gate rows, [1] q rows, [2] P rows, [3] x2 rows ----
+  // ---- row tables: [0] LSTM gate rows, [1] q rows, [2] P rows, [3] x2 rows (S consumers: 8 real + 8 zero) ----
   std::vector<int32_t> rows((size_t)4 * kG * 32, -1);
   for (int c = 0; c < kG; ++c) {
     for (int col = 0; col < 32; ++col) rows[(0 * kG + c) * 32 + col] = (col & 3) * 1024 + c * 8 + (col >> 2);
@@ -894,11 +924,11 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
     return T2_OK;
   };
   T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, 0, 4, r_lstm, 0, 0));            // E0: att <- x2
-  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, 0, 16, r_lstm, 1, 0));                   // E1: dec <- ah
-  T2_TRY(pack(m->w[W_ARNN_WHH], kARnn, 0, 16, r_lstm, 1, 1));                 //     att' <- ah
+  T2_TRY(pack(m->w[W_ARNN_WHH], kARnn, 0, 16, r_lstm, 1, 0));                 // E1: att' <- ah
+  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, 0, 16, r_lstm, 1, 1));                   //     dec <- ah
   T2_TRY(pack(m->w[W_ATT_QUERY], kARnn, 0, 16, r_q, 1, 2));                   //     q <- ah
-  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, kARnn, 8, r_lstm, 2, 0));                // E2: dec <- ctx
-  T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, kPre, 8, r_lstm, 2, 1));         //     att' <- ctx
+  T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, kPre, 8, r_lstm, 2, 0));         // E2: att' <- ctx
+  T2_TRY(pack(m->w[W_DRNN_WIH], kdc, kARnn, 8, r_lstm, 2, 1));                //     dec <- ctx
   T2_TRY(pack(pk->wp_all, kdc, kDRnn, 8, r_p, 2, 2));                         //     P <- ctx
   T2_TRY(pack(m->w[W_DRNN_WHH], kDRnn, 0, 16, r_lstm, 3, 0));                 // E3: dec' <- dh
   T2_TRY(pack(pk->wp_all, kdc, 0, 16, r_p, 3, 1));                            //     P <- dh
@@ -941,13 +971,13 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   p.weff_img = pk->weff_img; p.w_v = m->w[W_ATT_V];
   {
     const char* e = getenv("T2_L2_PIN_FRAC");   // fraction of weight-image lines kept with evict_last priority
-    p.l2_pin_frac = e ? (float)atof(e) : 1.0f;
+    p.l2_pin_frac = e ? (float)atof(e) : 0.5f;
   }
   p.memory = a->memory; p.pm = w.pm; p.mem_len = a->memory_lengths;
   p.prenet_keep = a->prenet_keep; p.att_keep = a->att_keep; p.dec_keep = a->dec_keep;
   p.mel = a->mel; p.gate = a->gate; p.align = a->align; p.mel_lengths = a->mel_lengths; p.n_steps = a->n_steps;
   p.ctrl = w.ctrl;
-  p.B = B; p.T = T; p.cap = cap; p.infer = a->mode == T2_MODE_INFER; p.training = a->training; p.passes = 3;
+  p.B = B; p.T = T; p.cap = cap; p.infer = a->mode == T2_MODE_INFER; p.training = a->training;
   p.gate_threshold = a->gate_threshold; p.score_mask_value = a->score_mask_value;
   p.p_att = m->cfg.p_attention_dropout; p.p_dec = m->cfg.p_decoder_dropout; p.seed = a->seed;
   if (!p.infer) {
@@ -955,32 +985,40 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   }
   const size_t smem = persistent_smem_bytes(T);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  int want = 8;
   {
     const char* e = getenv("T2_CLUSTER");      // 1 disables the TMA multicast of the activation stream
-    p.cluster = e ? atoi(e) : kCluster;
-    if (p.cluster != 1 && p.cluster != 2 && p.cluster != 4 && p.cluster != 8) p.cluster = kCluster;
+    if (e) want = atoi(e);
+    if (want != 1 && want != 2 && want != 4 && want != 8) want = 8;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attrs[2];
+  // largest cluster size for which all 128 CTAs are co-resident (GPCs of 16-20 SMs: 8 does not always fit)
+  for (p.cluster = want; p.cluster > 1; p.cluster >>= 1) {
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = p.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, decoder_persistent_kernel, &cfg) == cudaSuccess &&
+        max_clusters * p.cluster >= kG)
+      break;
+    (void)cudaGetLastError();
+  }
   int na = 0;
-  attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; ++na;   // co-residency of all 128 CTAs
   if (p.cluster > 1) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
     attrs[na].val.clusterDim.x = p.cluster; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1; ++na;
   }
+  attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; ++na;   // co-residency of all 128 CTAs
   cfg.attrs = attrs; cfg.numAttrs = na;
   cudaError_t le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
   if (le != cudaSuccess && p.cluster > 1) {
-    // some driver/runtime combinations reject cooperative + cluster launches: 128 CTAs at one CTA per
-    // SM are co-resident on a 148-SM part anyway (checked by occupancy below), so launch without the flag
+    // cooperative + cluster launch rejected: co-residency was established by the occupancy query above
     (void)cudaGetLastError();
-    int max_clusters = 0;
-    cfg.attrs = attrs + 1; cfg.numAttrs = 1;
-    T2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, decoder_persistent_kernel, &cfg));
-    if (max_clusters * p.cluster < kG)
-      return fail(T2_ERR_UNSUPPORTED, "persistent decoder: only %d clusters of %d CTAs can be co-resident", max_clusters, p.cluster);
+    cfg.numAttrs = 1;
     le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
   }
   if (le != cudaSuccess) return fail(T2_ERR_CUDA, "persistent decoder launch failed: %s", cudaGetErrorString(le));
@@ -989,11 +1027,12 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// self test of the tcgen05 engine: C (64 x N) = A (64 x K) . W (N x K)^T with the same run_event()
+// self test of the tcgen05 engine: C (64 x N) = 2 * A (64 x K) . W (N x K)^T with the same run_event()
+// (two accumulating passes over the ring) and the same hi/lo accumulator read-out as the decoder.
 // ---------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(kThreads, 1)
-selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int chunks, int passes, float* C, int N,
+selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int chunks, float* C, int N,
                 DecoderCtrl* ctrl) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1002,7 +1041,8 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   rg.stage0 = sp; sp += kStages * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
   rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
+  float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = rg.pol_w = ptx::policy_evict_last();
   rg.cs = 1; rg.rank = 0;
@@ -1016,20 +1056,28 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // run twice: the second run accumulates on top of the first (exercises the accumulate flag and
-  // the ring wrap-around); the host compares against 2 * A.W^T
-  run_event(rg, ep, x_img, w_img, chunks, 1u, passes, tmem_base, ctrl);
-  ptx::tc_fence_before();
-  __syncthreads();
-  run_event(rg, ep, x_img, w_img, chunks, 0u, passes, tmem_base, ctrl);
   const int quad = warp & 3, cg = warp >> 2;
   const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  for (int c = cg * 40; c < cg * 40 + 40; c += 8) ptx::tmem_zero8(t_lane + c);
+  ptx::tmem_wait_st();
+  ptx::tc_fence_before();
+  __syncthreads();
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl);
+  ptx::tc_fence_before();
+  __syncthreads();
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl);
+  const int row = (quad & 1) * 32 + lane;
+  float g[kHiCols / 8][8];
   for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
-    float g[8];
-    ptx::tmem_ld8(t_lane + c0, g);
-    if (lane < 16)
-      for (int j = 0; j < 8; ++j) C[(quad * 16 + lane) * N + c0 + j] = g[j];
+    acc_take8(t_lane, c0, g[c0 / 32]);
+    if (quad >= 2)
+      for (int j = 0; j < 8; ++j) s_xch[row * kHiCols + c0 + j] = g[c0 / 32][j];
   }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (quad < 2)
+    for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4))
+      for (int j = 0; j < 8; ++j) C[row * N + c0 + j] = g[c0 / 32][j] + s_xch[row * kHiCols + c0 + j];
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
@@ -1037,22 +1085,24 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
 }  // namespace
 
 int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s) {
-  if (N % 8 != 0 || N < 8 || N > 64 || K % kChunkK != 0 || K <= 0) return fail(T2_ERR_INVALID, "selftest_umma: N in {8..64 step 8}, K %% 64 == 0");
+  (void)passes;
+  if (N % 16 != 0 || N < 16 || N > kHiCols || K % kChunkK != 0 || K <= 0)
+    return fail(T2_ERR_INVALID, "selftest_umma: N in {16..80 step 16}, K %% 64 == 0");
   const int chunks = K / kChunkK;
   uint8_t *ximg = nullptr, *wimg = nullptr; DecoderCtrl* ctrl = nullptr;
   T2_CUDA(cudaMalloc((void**)&ximg, (size_t)chunks * kXChunkBytes));
   T2_CUDA(cudaMalloc((void**)&wimg, (size_t)chunks * N * 256));
   T2_CUDA(cudaMalloc((void**)&ctrl, sizeof(DecoderCtrl)));
   T2_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(DecoderCtrl), s));
-  CtaPlan hp; memset(&hp, 0, sizeof(hp));
-  hp.ev[0].ncons = 1; hp.ev[0].n[0] = N; hp.ev[0].col[0] = 0; hp.ev[0].w_bytes = N * 256; hp.ev[0].w_off = 0;
+  EventPlan ep; memset(&ep, 0, sizeof(ep));
+  ep.ncons = 1; ep.n[0] = N; ep.nrows = N; ep.col0 = 0; ep.w_bytes = N * 256; ep.w_off = 0;
   rows_to_image_kernel<<<dim3(chunks, 1), 256, 0, s>>>(A, K, kRows, K, 0, ximg, 0);
   T2_LAUNCH_CHECK();
   pack_rows_image_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
   T2_LAUNCH_CHECK();
-  const size_t smem = (size_t)kStages * kStageBytes + 16 * 8 + 64;
+  const size_t smem = (size_t)kStages * kStageBytes + 16 * 8 + 16 + (size_t)kRows * kHiCols * 4 + 64;
   T2_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  selftest_kernel<<<1, kThreads, smem, s>>>(ximg, wimg, hp.ev[0], chunks, passes, C, N, ctrl);
+  selftest_kernel<<<1, kThreads, smem, s>>>(ximg, wimg, ep, chunks, C, N, ctrl);
   T2_LAUNCH_CHECK();
   T2_CUDA(cudaStreamSynchronize(s));
   cudaFree(ximg); cudaFree(wimg); cudaFree(ctrl);

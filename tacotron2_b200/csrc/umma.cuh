@@ -147,6 +147,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// registers -> TMEM: zero 8 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, no swizzle ("interleaved" canonical layout):
 // core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; lbo = byte distance between core
