@@ -182,7 +182,7 @@ int    t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes,
                      float* C, void* stream);
 /* After a T2_IMPL_PERSISTENT run with the same args / workspace: SM cycles spent per phase of the
- * persistent kernel, summed over steps, on three sample CTAs (out_host[3][16]; phase list in
+ * persistent kernel, summed over steps, on three sample CTAs (out_host[3][24]; phase list in
  * decoder_persistent.cu).  Synchronises the device. */
 int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */

@@ -249,11 +249,12 @@ class Engine:
     def decoder_profile(self):
         """Per-phase SM cycles of the last persistent decoder run: dict phase -> [cta0, cta60, cta100]."""
         a = self._last_decoder_args[0]
-        out = (C.c_int64 * 48)()
+        out = (C.c_int64 * 72)()
         _capi.check(_capi.lib().t2_decoder_profile(C.byref(a), out))
         names = ["E0 x2->att gemm", "E0 epilogue(ah)", "B1", "E1 ah->dec/att/q gemm", "B2", "attention", "B3",
-                 "E2 ctx gemm", "E2 epilogue(dh)", "B4", "E3 dh gemm", "E3 epilogue(mel/x1)", "B5", "E4 x1 gemm+epi", "B6", "-"]
-        return {names[i]: [int(out[s * 16 + i]) for s in range(3)] for i in range(15)}
+                 "E2 ctx gemm", "E2 epilogue(dh)", "B4", "E3 dh gemm", "E3 epilogue(mel/x1)", "B5", "E4 x1 gemm+epi", "B6",
+                 "att:im2col", "att:mma", "att:energies", "att:softmax", "att:context"]
+        return {names[i]: [int(out[s * 24 + i]) for s in range(3)] for i in range(len(names))}
 
     def prenet(self, frames, keep=None):
         """frames (M, 80) -> (M, 256); keep (2, M, 256) uint8 or None."""

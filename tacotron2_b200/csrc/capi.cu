@@ -325,7 +325,7 @@ int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host) {
   DecoderWs w;
   T2_TRY(decoder_ws_carve(a, &w));
   T2_CUDA(cudaDeviceSynchronize());
-  T2_CUDA(cudaMemcpy(out_host, w.ctrl->prof, sizeof(long long) * 48, cudaMemcpyDeviceToHost));
+  T2_CUDA(cudaMemcpy(out_host, w.ctrl->prof, sizeof(long long) * 72, cudaMemcpyDeviceToHost));
   return T2_OK;
 }
 

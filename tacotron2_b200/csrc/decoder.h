@@ -14,7 +14,7 @@ struct DecoderCtrl {
   unsigned int bar_gen;
   int pad2_[2];
   int done[kMaxBatch];     // per-row stop latch
-  long long prof[3][16];   // cycles per phase of the persistent kernel, sampled on CTAs 0 / 60 / 100
+  long long prof[3][24];   // cycles per phase of the persistent kernel, sampled on CTAs 0 / 60 / 100
 };
 
 struct DecoderWs {

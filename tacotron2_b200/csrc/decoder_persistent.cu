@@ -287,9 +287,9 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
         const uint32_t ws = xs + kXChunkBytes;
 #pragma unroll
         for (int kk = 0; kk < kChunkK / 16; ++kk) {
-          const uint64_t a = ptx::make_smem_desc(xs + kk * 256, 128, 1024);              // [X_hi ; X_lo], M = 128
-          const uint64_t b_hi = ptx::make_smem_desc(ws + kk * 256, 128, 1024);
-          const uint64_t b_lo = ptx::make_smem_desc(ws + n * kChunkK * 2 + kk * 256, 128, 1024);
+          const uint64_t a = ptx::make_sw128_desc(xs + kk * 32);                          // [X_hi ; X_lo], M = 128
+          const uint64_t b_hi = ptx::make_sw128_desc(ws + kk * 32);
+          const uint64_t b_lo = ptx::make_sw128_desc(ws + n * kChunkK * 2 + kk * 32);
           ptx::umma_f16(d_hi, a, b_hi, idesc, 1u);
           ptx::umma_f16(d_lo, a, b_lo, idesc, 1u);
         }
@@ -536,12 +536,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
             if (kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
             split_fp16(v, hh[e], ll[e]);
           }
-          uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + g8 * 128 + (r & 7) * 16;
+          uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) * 16);
           *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
           *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
         }
         ptx::fence_proxy_async();
         __syncthreads();
+        T2_PROF(15);
         // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
         //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
         if (warp == 1) {
@@ -553,10 +554,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
               const uint32_t d = tmem_base + kColAtt + tile * 128;
 #pragma unroll
               for (int kk = 0; kk < kChunkK / 16; ++kk) {
-                const uint64_t a_hi = ptx::make_smem_desc(as + tile * 32768 + kk * 256, 128, 1024);
-                const uint64_t a_lo = ptx::make_smem_desc(as + tile * 32768 + 16384 + kk * 256, 128, 1024);
-                const uint64_t b_hi = ptx::make_smem_desc(bs + kk * 256, 128, 1024);
-                const uint64_t b_lo = ptx::make_smem_desc(bs + 16384 + kk * 256, 128, 1024);
+                const uint64_t a_hi = ptx::make_sw128_desc(as + tile * 32768 + kk * 32);
+                const uint64_t a_lo = ptx::make_sw128_desc(as + tile * 32768 + 16384 + kk * 32);
+                const uint64_t b_hi = ptx::make_sw128_desc(bs + kk * 32);
+                const uint64_t b_lo = ptx::make_sw128_desc(bs + 16384 + kk * 32);
                 ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
                 ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
                 ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
@@ -569,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
         rg.acc_phase ^= 1;
         ptx::tc_fence_after();
+        T2_PROF(16);
         // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
         //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
         {
@@ -614,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         ptx::tc_fence_before();
         __syncthreads();
+        T2_PROF(17);
       }
       const int len = p.mem_len ? p.mem_len[b] : T;
       float mx = -INFINITY;                                     // mask + softmax         model.py:79-82
@@ -646,6 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (ahalf == 0) p.align[((long)b * p.cap + t) * T + j] = a;
       }
       __syncthreads();
+      T2_PROF(18);
       {                                                           // context = aw . memory  model.py:83-84
         float* scr = reinterpret_cast<float*>(rg.stage0);         // [8][256] partial sums (ring is idle)
         const int c4 = tid & 63, jg = tid >> 6;                   // 64 float4 = this CTA's 256 columns; 8 j-groups
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           store_split2(p.ctx_img, b, ahalf * (kEnc / 2) + col, v0, v1);
         }
       }
+      T2_PROF(19);
     }
     T2_PROF(5);
     grid_barrier(ctrl, bar_target);                                            // B3: ctx_t complete

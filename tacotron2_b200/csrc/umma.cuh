@@ -166,6 +166,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
+// K-major SWIZZLE_128B descriptor: rows are 128 contiguous bytes (64 fp16 = one K chunk), 8-row atoms of
+// 1024 bytes, 16-byte units XOR-swizzled by the row index inside the atom; the atom base must be
+// 1024-byte aligned.  A 16-wide K step advances the start address by 32 bytes.  (cute::UMMA K-major B128)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                       // leading byte offset: unused for swizzled K-major (1)
+  d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  return d;
+}
 // instruction descriptor kind::f16: D fp32, A/B fp16, both K-major
 __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -176,13 +188,14 @@ __device__ __forceinline__ uint32_t make_idesc_f16_m64(uint32_t N) { return make
 
 // ---- operand images ---------------------------------------------------------------------------------
 // A K-chunk (64 columns) of an operand with R rows is stored as two planes [hi][lo] of fp16, each in
-// the canonical no-swizzle K-major layout: element (r, k) at
-//     (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2      bytes
+// the tcgen05 K-major SWIZZLE_128B layout: row r is 128 contiguous bytes, rows are grouped in 8-row
+// atoms of 1024 bytes, and the 16-byte unit (k/8) of row r sits at unit position (k/8) ^ (r%8):
+//     byte(r, k) = (r/8)*1024 + (r%8)*128 + (((k/8) ^ (r%8)) * 16) + (k%8)*2
 // so one plane is R*128 bytes and one contiguous bulk copy brings the whole chunk into shared memory
-// ready for tcgen05.mma (LBO = 128, SBO = 1024).
+// ready for tcgen05.mma (atoms 1024-byte aligned in shared memory).
 constexpr int kChunkK = 64;
 __host__ __device__ inline uint32_t img_elem_offset(int r, int k) {   // in fp16 elements within a plane
-  return (uint32_t)((r >> 3) * 512 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7));
+  return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((((k >> 3) ^ (r & 7)) & 7) * 8) + (k & 7));
 }
 __device__ __forceinline__ void split_fp16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
