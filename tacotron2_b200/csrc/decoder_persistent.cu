@@ -18,10 +18,11 @@
 //     NEXT step is computed from [dh; ctx] directly (model.py:97-100, 373-378, 449).
 //   * fp32-grade arithmetic on fp16 tensor cores: every operand is split x = hi + lo (two fp16).  The
 //     activation chunk image [hi rows 0-63 | lo rows 64-127] is ONE M=128 A operand; the weight rows of
-//     all consumers of an event are concatenated along N, once as hi and once as lo; two MMAs per
-//     16-wide K step give all four partial products (hi.hi, lo.hi, hi.lo, lo.lo) in fp32:
-//        D_hi[128 x N] += [X_hi; X_lo] . W_hi^T      D_lo[128 x N] += [X_hi; X_lo] . W_lo^T
-//     gates[r] = D_hi[r] + D_lo[r] + D_hi[64+r] + D_lo[64+r]  (summed in the epilogue).
+//     all consumers of an event are concatenated along N as [W_hi ; W_lo] per consumer, so ONE MMA per
+//     16-wide K step gives all four partial products (hi.hi, lo.hi, hi.lo, lo.lo) in fp32 (the SS-mode
+//     MMA is bound by its 128-row A read, not by N: measured ~125 cycles for any N <= 160):
+//        D[128 x 2N] += [X_hi; X_lo] . [W_hi; W_lo]^T
+//     gates[r] = D[r][hi] + D[r][lo] + D[64+r][hi] + D[64+r][lo]  (summed in the epilogue).
 //     Accumulators are always accumulated into and zeroed by the epilogue that consumed them.
 //   * location-sensitive attention (model.py:43-86): location conv + dense are fused into one 62-tap
 //     filter bank evaluated as a tensor-core GEMM over an im2col image of the previous / cumulative
@@ -47,8 +48,10 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
 constexpr int kRows = 64;             // batch rows per launch (zero padded)
 constexpr int kXChunkBytes = 2 * kRows * kChunkK * 2;    // [hi 64 rows | lo 64 rows] x 64 k fp16 = 16 KiB
-constexpr int kColA = 0, kColD = 32, kColS = 64;         // hi-part accumulator columns: att | dec | shared slot
-constexpr int kHiCols = 80;                               // lo-part accumulators live at +kHiCols
+// accumulator columns: each consumer owns [hi-part n | lo-part n]: att 0-63, dec 64-127, shared slot 128-159
+constexpr int kColA = 0, kColD = 64, kColS = 128;
+constexpr int kNA = 32, kND = 32, kNS = 16;               // weight rows (hi) per consumer
+constexpr int kHiCols = 80;                               // max weight rows of one event (hi) -> MMA N <= 160
 constexpr int kColAtt = 160;                              // attention pa accumulators: 2 tiles x 128 columns
 constexpr int kTmemCols = 512;
 constexpr int kWStageMax = 2 * kHiCols * kChunkK * 2;    // hi + lo planes of up to 80 weight rows = 20 KiB
@@ -62,9 +65,9 @@ constexpr unsigned long long kWatchdogCycles = 1ull << 32;   // ~2 s
 
 struct EventPlan {
   uint32_t w_off;       // byte offset of this CTA's first chunk in the W image buffer
-  uint32_t w_bytes;     // W bytes per chunk = 2 planes x nrows x 128
-  int32_t nrows;        // weight rows of all consumers (MMA N); 0 = this CTA skips the event
-  int32_t col0;         // hi-part accumulator column of the first consumer
+  uint32_t w_bytes;     // W bytes per chunk = 2 x nrows x 128
+  int32_t nrows;        // hi weight rows of all consumers (MMA N = 2 x nrows); 0 = this CTA skips the event
+  int32_t col0;         // accumulator column of the first consumer
   int32_t ncons;
   int32_t n[3];         // rows per consumer (packing only)
 };
@@ -141,18 +144,17 @@ __global__ void pack_consumer_kernel(const float* __restrict__ src, int ld, int 
   const EventPlan& ep = plans[cta].ev[ev];
   if (cons >= ep.ncons) return;
   const int n = ep.n[cons];
-  int roff = 0;
-  for (int i = 0; i < cons; ++i) roff += ep.n[i];
-  __half* hi = reinterpret_cast<__half*>(wimg + ep.w_off + (size_t)chunk * ep.w_bytes);
-  __half* lo = hi + ep.nrows * 64;
+  int roff = 0;                               // rows before this consumer: [hi | lo] of each earlier one
+  for (int i = 0; i < cons; ++i) roff += 2 * ep.n[i];
+  __half* img = reinterpret_cast<__half*>(wimg + ep.w_off + (size_t)chunk * ep.w_bytes);
   for (int i = threadIdx.x; i < n * 64; i += blockDim.x) {
     const int r = i >> 6, k = i & 63;
     const int srow = rows_tab[cta * 32 + r];
     const float v = srow >= 0 ? src[(long)srow * ld + kcol0 + chunk * 64 + k] : 0.f;
     __half h, l;
     split_fp16(v, h, l);
-    const uint32_t e = img_elem_offset(roff + r, k);
-    hi[e] = h; lo[e] = l;
+    img[img_elem_offset(roff + r, k)] = h;
+    img[img_elem_offset(roff + n + r, k)] = l;
   }
 }
 
@@ -249,7 +251,7 @@ struct Ring {
 };
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight rows through the ring
-// and issues the MMAs (2 per 16-wide K step).  Called by all threads; returns after the accumulators are
+// and issues the MMAs (1 per 16-wide K step).  Called by all threads; returns after the accumulators are
 // complete.  Every MMA accumulates (the epilogues zero what they consume).
 __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
                                           const uint8_t* w_img, int chunks, uint32_t tmem_base,
@@ -277,9 +279,8 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t n = (uint32_t)ep.nrows;
-      const uint32_t idesc = ptx::make_idesc_f16(128, n);
-      const uint32_t d_hi = tmem_base + (uint32_t)ep.col0, d_lo = d_hi + kHiCols;
+      const uint32_t idesc = ptx::make_idesc_f16(128, 2u * (uint32_t)ep.nrows);
+      const uint32_t d = tmem_base + (uint32_t)ep.col0;
       for (int i = 0; i < chunks; ++i) {
         mbar_wait(&rg.full[rg.c_stage], rg.c_phase, ctrl, 201);
         ptx::tc_fence_after();
@@ -288,10 +289,8 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
 #pragma unroll
         for (int kk = 0; kk < kChunkK / 16; ++kk) {
           const uint64_t a = ptx::make_sw128_desc(xs + kk * 32);                          // [X_hi ; X_lo], M = 128
-          const uint64_t b_hi = ptx::make_sw128_desc(ws + kk * 32);
-          const uint64_t b_lo = ptx::make_sw128_desc(ws + n * kChunkK * 2 + kk * 32);
-          ptx::umma_f16(d_hi, a, b_hi, idesc, 1u);
-          ptx::umma_f16(d_lo, a, b_lo, idesc, 1u);
+          const uint64_t b = ptx::make_sw128_desc(ws + kk * 32);                          // [W_hi ; W_lo] per consumer
+          ptx::umma_f16(d, a, b, idesc, 1u);
         }
         if (rg.cs == 1) ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
         else ptx::umma_commit_mc(&rg.empty[rg.c_stage], (uint16_t)((1u << rg.cs) - 1u));
@@ -306,15 +305,16 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
   ptx::tc_fence_after();
 }
 
-// this lane's 8 accumulator columns: hi-part + lo-part, then zero both (they are consumed)
-__device__ __forceinline__ void acc_take8(uint32_t t_lane, int col, float* s) {
+// this lane's 8 accumulator columns of a consumer with n hi-columns at `base`: hi-part + lo-part, then
+// zero both (they are consumed)
+__device__ __forceinline__ void acc_take8(uint32_t t_lane, int base, int n, int col, float* s) {
   float a[8], b[8];
-  ptx::tmem_ld8(t_lane + col, a);
-  ptx::tmem_ld8(t_lane + kHiCols + col, b);
+  ptx::tmem_ld8(t_lane + base + col, a);
+  ptx::tmem_ld8(t_lane + base + n + col, b);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = a[i] + b[i];
-  ptx::tmem_zero8(t_lane + col);
-  ptx::tmem_zero8(t_lane + kHiCols + col);
+  ptx::tmem_zero8(t_lane + base + col);
+  ptx::tmem_zero8(t_lane + base + n + col);
   ptx::tmem_wait_st();
 }
 
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   } while (0)
   // LSTM epilogue shared by both cells: take the 8 gate columns (2 units x i,f,g,o) of this lane,
   // combine hi-row and lo-row partial sums through shared memory, return them in g[] for batch rows
-#define T2_TAKE_GATES(colbase, g)                                                        \
+#define T2_TAKE_GATES(colbase, n_, g)                                                        \
   do {                                                                                   \
-    acc_take8(t_lane, (colbase) + cg * 8, g);                                            \
+    acc_take8(t_lane, (colbase), (n_), cg * 8, g);                                       \
     if (is_lo) {                                                                         \
       _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) s_xch[row * kXchStride + cg * 8 + i_] = g[i_]; \
     }                                                                                    \
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       run_event(rg, plan.ev[0], x2, p.wimg, 4, tmem_base, ctrl);
       T2_PROF(0);
       float g[8];
-      T2_TAKE_GATES(kColA, g);
+      T2_TAKE_GATES(kColA, kNA, g);
       if (erow) {
         float hv[2];
 #pragma unroll
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl);
       if (has_q) {
         float g[8];
-        if (cg == 0) acc_take8(t_lane, kColS, g);
+        if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
         if (cg == 0 && is_lo) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, tmem_base, ctrl);
       T2_PROF(7);
       float g[8];
-      T2_TAKE_GATES(kColD, g);
+      T2_TAKE_GATES(kColD, kND, g);
       if (erow) {
         float hv[2];
 #pragma unroll
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       T2_PROF(10);
       if (tid == 0) *s_live = 0;
       float g[8];
-      if (has_p && cg == 0) acc_take8(t_lane, kColS, g);
+      if (has_p && cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
       if (has_p && cg == 0 && is_lo) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl);
       if (has_x2) {
         float g[8];
-        if (cg == 0) acc_take8(t_lane, kColS, g);
+        if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
         if (cg == 0 && is_lo) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
@@ -1074,7 +1074,7 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   const int row = (quad & 1) * 32 + lane;
   float g[kHiCols / 8][8];
   for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
-    acc_take8(t_lane, c0, g[c0 / 32]);
+    acc_take8(t_lane, 0, N, c0, g[c0 / 32]);
     if (quad >= 2)
       for (int j = 0; j < 8; ++j) s_xch[row * kHiCols + c0 + j] = g[c0 / 32][j];
   }
@@ -1091,8 +1091,8 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
 
 int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s) {
   (void)passes;
-  if (N % 16 != 0 || N < 16 || N > kHiCols || K % kChunkK != 0 || K <= 0)
-    return fail(T2_ERR_INVALID, "selftest_umma: N in {16..80 step 16}, K %% 64 == 0");
+  if (N % 8 != 0 || N < 8 || N > kHiCols || K % kChunkK != 0 || K <= 0)
+    return fail(T2_ERR_INVALID, "selftest_umma: N in {8..80 step 8}, K %% 64 == 0");
   const int chunks = K / kChunkK;
   uint8_t *ximg = nullptr, *wimg = nullptr; DecoderCtrl* ctrl = nullptr;
   T2_CUDA(cudaMalloc((void**)&ximg, (size_t)chunks * kXChunkBytes));

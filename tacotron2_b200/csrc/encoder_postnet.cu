@@ -171,6 +171,98 @@ enc_lstm_step_kernel(const float* __restrict__ gin,   // (B, T, 2048) W_ih x + b
   }
 }
 
+// Persistent variant of the recurrence: ONE cooperative launch runs all T steps of both directions.
+// 128 CTAs = 2 directions x 64 unit blocks of 4 hidden units (16 gate rows); the CTA's W_hh slice stays
+// in shared memory for the whole sequence, h is exchanged through a double-buffered global array and a
+// grid-wide barrier (monotonic counter) per step.  256 threads = 64 batch rows x 4 units; each thread
+// owns the 4 gates of ONE (row, unit) pair, so the cell state lives in a register.
+struct EncLstmCtrl { unsigned int bar_count; unsigned int pad_[3]; };
+
+__global__ void __launch_bounds__(256, 1)
+enc_lstm_persistent_kernel(const float* __restrict__ gin, const float* __restrict__ whh_f,
+                           const float* __restrict__ whh_r, float* __restrict__ hbuf,   // (2 buffers, 2 dirs, B, 256)
+                           float* __restrict__ memory, const int32_t* __restrict__ lengths, int B, int T,
+                           EncLstmCtrl* ctrl) {
+  extern __shared__ float sm[];
+  float* ws = sm;                        // [64 k4][16 rows][4]   (row = gate*4 + unit_local)
+  float* hs = sm + kEncH * 16;           // [64 k4][64 batch][4]
+  const int cta = blockIdx.x, dir = cta >> 6, ub = cta & 63;
+  const int tid = threadIdx.x;
+  const float* whh = dir == 0 ? whh_f : whh_r;
+  for (int i = tid; i < 16 * (kEncH / 4); i += 256) {
+    const int r = i / (kEncH / 4), k4 = i % (kEncH / 4);
+    const int gate = r >> 2, ul = r & 3;
+    const float4 v = reinterpret_cast<const float4*>(whh + ((long)gate * kEncH + ub * 4 + ul) * kEncH)[k4];
+    reinterpret_cast<float4*>(ws)[k4 * 16 + r] = v;
+  }
+  const int b = tid & 63, ul = tid >> 6;             // batch row, local unit
+  const int unit = ub * 4 + ul;
+  float c = 0.f, hprev = 0.f;
+  unsigned int target = 0;
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+    const float* hin = hbuf + ((long)(step & 1) * 2 + dir) * B * kEncH;
+    float* hout = hbuf + ((long)((step + 1) & 1) * 2 + dir) * B * kEncH;
+    // gate pre-activations from the input projection (issued first: their latency hides behind the GEMV)
+    float gi4[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool live = b < B;
+    const bool valid = live && (lengths == nullptr || t < lengths[b]);
+    if (live) {
+      const float* gp = gin + ((long)b * T + t) * (8 * kEncH) + dir * 4 * kEncH + unit;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gi4[g] = __ldg(gp + g * kEncH);
+    }
+    for (int i = tid; i < 64 * (kEncH / 4); i += 256) {       // h_(t-1) of all rows -> [k4][b][4]
+      const int bb = i / (kEncH / 4), k4 = i % (kEncH / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bb < B) v = __ldcg(reinterpret_cast<const float4*>(hin + (long)bb * kEncH) + k4);
+      reinterpret_cast<float4*>(hs)[k4 * 64 + bb] = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k4 = 0; k4 < kEncH / 4; ++k4) {
+      const float4 hv = reinterpret_cast<const float4*>(hs)[k4 * 64 + b];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 wv = reinterpret_cast<const float4*>(ws)[k4 * 16 + g * 4 + ul];
+        acc[g] = fmaf(wv.x, hv.x, acc[g]); acc[g] = fmaf(wv.y, hv.y, acc[g]);
+        acc[g] = fmaf(wv.z, hv.z, acc[g]); acc[g] = fmaf(wv.w, hv.w, acc[g]);
+      }
+    }
+    if (live) {
+      float hn = hprev;
+      if (valid) {
+        const float gi = 1.f / (1.f + expf(-(acc[0] + gi4[0])));
+        const float gf = 1.f / (1.f + expf(-(acc[1] + gi4[1])));
+        const float gg = tanhf(acc[2] + gi4[2]);
+        const float go = 1.f / (1.f + expf(-(acc[3] + gi4[3])));
+        c = gf * c + gi * gg;
+        hn = go * tanhf(c);
+      }
+      hprev = hn;
+      hout[(long)b * kEncH + unit] = hn;
+      memory[((long)b * T + t) * kEnc + dir * kEncH + unit] = valid ? hn : 0.f;
+    }
+    // grid barrier (monotonic counter, red.release / ld.acquire)
+    __syncthreads();
+    target += gridDim.x;
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
+      const unsigned long long t0 = clock64();
+      while (true) {
+        unsigned int cnt;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cnt) : "l"(&ctrl->bar_count) : "memory");
+        if ((int)(cnt - target) >= 0) break;
+        if (clock64() - t0 > (1ull << 32)) __trap();
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -228,6 +320,7 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
   float* cbuf = (float*)p; p += align256((size_t)2 * B * kEncH * 4);
   float* scale = (float*)p; p += align256(kEnc * 4);
   float* shift = (float*)p; p += align256(kEnc * 4);
+  EncLstmCtrl* lctrl = (EncLstmCtrl*)p; p += 256;
 
   if (a->embedded) {
     T2_CUDA(cudaMemcpyAsync(x0, a->embedded, (size_t)B * T * kEnc * 4, cudaMemcpyDeviceToDevice, s));
@@ -250,6 +343,21 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
   }
   T2_CUDA(cudaMemsetAsync(hbuf0, 0, (size_t)2 * B * kEncH * 4, s));
   T2_CUDA(cudaMemsetAsync(cbuf, 0, (size_t)2 * B * kEncH * 4, s));
+  if (B <= 64 && m->sm_count >= 128 && getenv("T2_ENC_LSTM_STEPWISE") == nullptr) {
+    // persistent recurrence: one cooperative launch for all T steps of both directions
+    T2_CUDA(cudaMemsetAsync(hbuf1, 0, (size_t)2 * B * kEncH * 4, s));
+    T2_CUDA(cudaMemsetAsync(lctrl, 0, 256, s));
+    float* hb = hbuf0;   // hbuf0 and hbuf1 are adjacent (2 x (2, B, 256) when align256 adds no padding)
+    if (hbuf1 != hbuf0 + (size_t)2 * B * kEncH) return fail(T2_ERR_INVALID, "encoder: h buffers not adjacent");
+    const size_t psm = (size_t)(kEncH * 16 + kEncH * 64) * sizeof(float);
+    T2_CUDA(cudaFuncSetAttribute(enc_lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    const float* whf = m->w[W_ENC_LSTM + 1]; const float* whr = m->w[W_ENC_LSTM + 5];
+    const int32_t* lens = a->lengths; float* mem = a->memory; int Bv = B, Tv = T;
+    void* args[] = {(void*)&gin, (void*)&whf, (void*)&whr, (void*)&hb, (void*)&mem, (void*)&lens, (void*)&Bv, (void*)&Tv, (void*)&lctrl};
+    T2_CUDA(cudaLaunchCooperativeKernel((void*)enc_lstm_persistent_kernel, dim3(128), dim3(256), args, psm, s));
+    g_launch_count++;
+    return T2_OK;
+  }
   const size_t smem = (64 * kEncH + 64 * (kEncH + 1)) * sizeof(float);
   T2_CUDA(cudaFuncSetAttribute(enc_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* hin = hbuf0; float* hout = hbuf1;

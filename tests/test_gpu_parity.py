@@ -39,7 +39,7 @@ def test_native_library_is_loaded():
 
 
 @pytest.mark.parametrize("passes,tol", [(3, 2e-5), (1, 2e-3)])
-@pytest.mark.parametrize("N,K", [(32, 256), (16, 64), (64, 1024), (80, 192), (48, 1024)])
+@pytest.mark.parametrize("N,K", [(32, 256), (8, 64), (64, 1024), (80, 192), (48, 1024)])
 def test_umma_split_gemm_selftest(N, K, passes, tol):
     """tcgen05 engine of the persistent decoder: C = 2 * A (64xK) . W (NxK)^T (two accumulating runs)."""
     g = torch.Generator().manual_seed(N * 1000 + K)
