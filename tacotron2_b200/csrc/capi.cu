@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include "conv_tc.h"
 #include "decoder.h"
 #include "gemm_f32.cuh"
 
@@ -90,6 +91,13 @@ int pack_model(T2Model* m, cudaStream_t s) {
   if (!m->zeros) {
     T2_TRY(dmalloc(&m->zeros, (size_t)8192));
     T2_CUDA(cudaMemsetAsync(m->zeros, 0, 8192 * 4, s));
+  }
+  // tensor-core conv / GEMM weight images
+  for (int i = 0; i < 3; ++i) T2_TRY(tc_pack_weights(m->w[W_ENC_CONV0 + 7 * i], kEnc, kEnc, kConvK, 256, &m->tc_enc_conv[i], s));
+  T2_TRY(tc_pack_weights(m->enc_lstm_wih, 8 * kEncH, kEnc, 1, 256, &m->tc_enc_wih, s));
+  for (int i = 0; i < 5; ++i) {
+    const int ci = i == 0 ? kMel : kPost, co = i == 4 ? kMel : kPost;
+    T2_TRY(tc_pack_weights(m->w[W_POST_CONV0 + 7 * i], co, ci, kConvK, i == 4 ? 80 : 256, &m->tc_post_conv[i], s));
   }
   T2_TRY(persistent_pack_create(m, s));
   return T2_OK;
@@ -217,6 +225,9 @@ int t2_model_destroy(T2Model* m) {
   for (int i = 0; i < 5; ++i) cudaFree(m->post_conv_w[i]);
   cudaFree(m->enc_lstm_wih); cudaFree(m->enc_lstm_b); cudaFree(m->arnn_b); cudaFree(m->drnn_b);
   cudaFree(m->projgate_w); cudaFree(m->projgate_b); cudaFree(m->zeros);
+  for (int i = 0; i < 3; ++i) cudaFree(m->tc_enc_conv[i]);
+  for (int i = 0; i < 5; ++i) cudaFree(m->tc_post_conv[i]);
+  cudaFree(m->tc_enc_wih);
   persistent_pack_destroy(m);
   delete m;
   return T2_OK;

@@ -1,5 +1,8 @@
 // Encoder (model.py:149-201) and Postnet (model.py:103-146): v0 implementation on the fp32 SIMT
 // GEMM engine with channels-last activations (conv1d == GEMM over K = taps x Cin).
+#include <stdlib.h>
+
+#include "conv_tc.h"
 #include "gemm_f32.cuh"
 #include "model.h"
 
@@ -266,10 +269,12 @@ enc_lstm_persistent_kernel(const float* __restrict__ gin, const float* __restric
 // ---- host side ----------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static bool use_tc() { const char* e = getenv("T2_CONV_IMPL"); return !(e && e[0] == 's'); }   // "simt" selects the fp32 SIMT path
+
 size_t encoder_ws_bytes(int B, int T) {
   const size_t act = align256((size_t)B * T * kEnc * 4);
   return 2 * act + align256((size_t)B * T * 8 * kEncH * 4) + 3 * align256((size_t)2 * B * kEncH * 4) +
-         2 * align256(kEnc * 4) + 1024;
+         2 * align256(8 * kEncH * 4) + 1024 + 2 * align256(tc_planes_bytes(B, T, kEnc));
 }
 
 static int conv_bn_layer(T2Model* m, const float* x, float* y, int B, int T, int cin, int cout,
@@ -318,28 +323,53 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
   float* hbuf0 = (float*)p; p += align256((size_t)2 * B * kEncH * 4);
   float* hbuf1 = (float*)p; p += align256((size_t)2 * B * kEncH * 4);
   float* cbuf = (float*)p; p += align256((size_t)2 * B * kEncH * 4);
-  float* scale = (float*)p; p += align256(kEnc * 4);
-  float* shift = (float*)p; p += align256(kEnc * 4);
+  float* scale = (float*)p; p += align256(8 * kEncH * 4);
+  float* shift = (float*)p; p += align256(8 * kEncH * 4);
   EncLstmCtrl* lctrl = (EncLstmCtrl*)p; p += 256;
+  p = (char*)align256((size_t)p);
+  __half* pl0 = (__half*)p; p += align256(tc_planes_bytes(B, T, kEnc));
+  __half* pl1 = (__half*)p; p += align256(tc_planes_bytes(B, T, kEnc));
+  const bool tc = use_tc() && !a->training;
 
-  if (a->embedded) {
-    T2_CUDA(cudaMemcpyAsync(x0, a->embedded, (size_t)B * T * kEnc * 4, cudaMemcpyDeviceToDevice, s));
+  if (tc) {
+    // tensor-core path: planes -> 3 x (conv k5 + folded BN + ReLU) -> LSTM input projection (fp32 rows)
+    if (a->embedded) T2_TRY(tc_rows_to_planes(a->embedded, (long)T * kEnc, kEnc, kEnc, nullptr, B, T, pl0, s));
+    else T2_TRY(tc_embed_to_planes(a->text, m->w[W_EMB], m->cfg.n_symbols, B, T, pl0, s));
+    __half* cur = pl0; __half* nxt = pl1;
+    for (int i = 0; i < 3; ++i) {                                                           // model.py:174-175, 194
+      const int wb = W_ENC_CONV0 + 7 * i;
+      T2_TRY(tc_fold_bn(m->w[wb + 1], m->w[wb + 2], m->w[wb + 3], m->w[wb + 4], m->w[wb + 5], m->cfg.bn_eps, scale, shift, kEnc, s));
+      TcConvArgs c; memset(&c, 0, sizeof(c));
+      c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_conv[i]; c.taps = kConvK; c.B = B; c.T = T; c.cout = kEnc; c.nt_rows = 256;
+      c.scale = scale; c.shift = shift; c.act = 1; c.out_mode = 0; c.out_planes = nxt;
+      T2_TRY(tc_conv(c, s));
+      __half* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    T2_TRY(tc_fold_bn(m->enc_lstm_b, nullptr, nullptr, nullptr, nullptr, 0.f, scale, shift, 8 * kEncH, s));
+    TcConvArgs c; memset(&c, 0, sizeof(c));
+    c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_wih; c.taps = 1; c.B = B; c.T = T; c.cout = 8 * kEncH; c.nt_rows = 256;
+    c.scale = scale; c.shift = shift; c.act = 0; c.out_mode = 1; c.out_f32 = gin; c.ldo = 8 * kEncH;
+    T2_TRY(tc_conv(c, s));
   } else {
-    embed_kernel<<<B * T, 128, 0, s>>>(a->text, m->w[W_EMB], x0, B * T, m->cfg.n_symbols);   // model.py:503/518
-    T2_LAUNCH_CHECK();
-  }
-  float* cur = x0; float* nxt = x1;
-  for (int i = 0; i < 3; ++i) {                                                             // model.py:174-175
-    const uint8_t* keep = (a->training && a->keep) ? a->keep + (size_t)i * B * kEnc * T : nullptr;
-    T2_TRY(conv_bn_layer(m, cur, nxt, B, T, kEnc, kEnc, m->enc_conv_w[i], W_ENC_CONV0 + 7 * i, ACT_RELU,
-                         a->training, keep, a->seed, 1000 + i, scale, shift, 0, nullptr, nullptr, s));
-    float* tmp = cur; cur = nxt; nxt = tmp;
-  }
-  {  // W_ih x + b_ih + b_hh for every time step and both directions
-    GemmArgs g;
-    g.seg[0] = {cur, kEnc, m->enc_lstm_wih, kEnc, kEnc};
-    g.M = B * T; g.N = 8 * kEncH; g.C = gin; g.ldc = 8 * kEncH; g.bias = m->enc_lstm_b;
-    T2_TRY(gemm_f32(g, s));
+    if (a->embedded) {
+      T2_CUDA(cudaMemcpyAsync(x0, a->embedded, (size_t)B * T * kEnc * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      embed_kernel<<<B * T, 128, 0, s>>>(a->text, m->w[W_EMB], x0, B * T, m->cfg.n_symbols);   // model.py:503/518
+      T2_LAUNCH_CHECK();
+    }
+    float* cur = x0; float* nxt = x1;
+    for (int i = 0; i < 3; ++i) {                                                             // model.py:174-175
+      const uint8_t* keep = (a->training && a->keep) ? a->keep + (size_t)i * B * kEnc * T : nullptr;
+      T2_TRY(conv_bn_layer(m, cur, nxt, B, T, kEnc, kEnc, m->enc_conv_w[i], W_ENC_CONV0 + 7 * i, ACT_RELU,
+                           a->training, keep, a->seed, 1000 + i, scale, shift, 0, nullptr, nullptr, s));
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    {  // W_ih x + b_ih + b_hh for every time step and both directions
+      GemmArgs g;
+      g.seg[0] = {cur, kEnc, m->enc_lstm_wih, kEnc, kEnc};
+      g.M = B * T; g.N = 8 * kEncH; g.C = gin; g.ldc = 8 * kEncH; g.bias = m->enc_lstm_b;
+      T2_TRY(gemm_f32(g, s));
+    }
   }
   T2_CUDA(cudaMemsetAsync(hbuf0, 0, (size_t)2 * B * kEncH * 4, s));
   T2_CUDA(cudaMemsetAsync(cbuf, 0, (size_t)2 * B * kEncH * 4, s));
@@ -371,7 +401,8 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
 }
 
 size_t postnet_ws_bytes(int B, int T) {
-  return 2 * align256((size_t)B * T * kPost * 4) + align256((size_t)B * T * kMel * 4) + 2 * align256(kPost * 4) + 1024;
+  return 2 * align256((size_t)B * T * kPost * 4) + align256((size_t)B * T * kMel * 4) + 2 * align256(kPost * 4) + 1024 +
+         2 * align256(tc_planes_bytes(B, T, kPost));
 }
 
 int postnet_forward(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
@@ -385,6 +416,28 @@ int postnet_forward(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
   float* xin = (float*)p; p += align256((size_t)B * T * kMel * 4);
   float* scale = (float*)p; p += align256(kPost * 4);
   float* shift = (float*)p; p += align256(kPost * 4);
+  p = (char*)align256((size_t)p);
+  __half* pl0 = (__half*)p; p += align256(tc_planes_bytes(B, T, kPost));
+  __half* pl1 = (__half*)p; p += align256(tc_planes_bytes(B, T, kPost));
+  if (use_tc() && !a->training) {
+    // tensor-core path (model.py:141-146 + residual :511/:524): mel -> planes -> 4 x (conv+BN+tanh) -> conv+BN (+mel)
+    const long bs = a->mel_batch_stride ? a->mel_batch_stride : (long)T * kMel;
+    T2_TRY(tc_rows_to_planes(a->mel, bs, kMel, 128, a->lengths, B, T, pl0, s));
+    __half* cur = pl0; __half* nxt = pl1;
+    for (int i = 0; i < 5; ++i) {
+      const int wb = W_POST_CONV0 + 7 * i;
+      const int cout = i == 4 ? kMel : kPost;
+      T2_TRY(tc_fold_bn(m->w[wb + 1], m->w[wb + 2], m->w[wb + 3], m->w[wb + 4], m->w[wb + 5], m->cfg.bn_eps, scale, shift, cout, s));
+      TcConvArgs c; memset(&c, 0, sizeof(c));
+      c.in = cur; c.cin_pad = i == 0 ? 128 : kPost; c.wimg = m->tc_post_conv[i]; c.taps = kConvK; c.B = B; c.T = T;
+      c.cout = cout; c.nt_rows = i == 4 ? 80 : 256; c.scale = scale; c.shift = shift; c.act = i == 4 ? 0 : 2;
+      if (i < 4) { c.out_mode = 0; c.out_planes = nxt; }
+      else { c.out_mode = 2; c.out_f32 = a->mel_post; c.residual = a->add_residual ? a->mel : nullptr; c.res_batch_stride = bs; c.row_len = a->lengths; }
+      T2_TRY(tc_conv(c, s));
+      __half* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    return T2_OK;
+  }
   const long n_in = (long)B * T * kMel;
   mask_rows_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, s>>>(
       a->mel, a->mel_batch_stride ? a->mel_batch_stride : (long)T * kMel, xin, a->lengths, B, T, kMel);

@@ -19,6 +19,11 @@ struct T2Model {
   float* projgate_b = nullptr;   // (81)
   float* zeros = nullptr;        // >= 4096 zeros (go frame etc.)
 
+  // ---- tensor-core conv / GEMM weight images (conv_tc.cu) ----
+  uint8_t* tc_enc_conv[3] = {};  // (512, 512, 5)  n-tile 256
+  uint8_t* tc_enc_wih = nullptr; // (2048, 512)    n-tile 256, taps = 1
+  uint8_t* tc_post_conv[5] = {}; // n-tile 256 (layers 0-3), 80 (layer 4)
+
   // ---- packed operands of the persistent decoder kernel (owned; see decoder_persistent.cu) ----
   void* pk = nullptr;            // opaque PersistentPack*
 };
