@@ -181,6 +181,9 @@ int    t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_
  * (64 x K) x (N x K)^T problem and writes C (64 x N) fp32; used by tests/test_umma_gemm.py. */
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes,
                      float* C, void* stream);
+/* Micro-benchmark: SM cycles for `reps` back-to-back tcgen05.mma (M x N x 16, fp16, operands resident in
+ * shared memory) -> out_host[0] = issue cycles, out_host[1] = issue + completion cycles. */
+int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host);
 /* After a T2_IMPL_PERSISTENT run with the same args / workspace: SM cycles spent per phase of the
  * persistent kernel, summed over steps, on three sample CTAs (out_host[3][24]; phase list in
  * decoder_persistent.cu).  Synchronises the device. */

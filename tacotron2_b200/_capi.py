@@ -16,7 +16,7 @@ EXPORTS = [
     "t2_model_destroy", "t2_encoder_workspace_bytes", "t2_encoder_forward",
     "t2_decoder_workspace_bytes", "t2_decoder_run", "t2_prenet_forward",
     "t2_postnet_workspace_bytes", "t2_postnet_forward", "t2_infer_workspace_bytes", "t2_infer_host",
-    "t2_selftest_umma", "t2_kernel_launch_count", "t2_decoder_profile",
+    "t2_selftest_umma", "t2_kernel_launch_count", "t2_decoder_profile", "t2_selftest_mma_rate",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
                                 C.c_void_p, C.c_size_t, C.c_void_p]
     L.t2_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]
+    L.t2_selftest_mma_rate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
     L.t2_decoder_profile.argtypes = [C.POINTER(T2DecoderArgs), C.POINTER(C.c_int64)]
     if L.t2_abi_version() != 1:
         raise RuntimeError("libt2b200.so ABI version mismatch")

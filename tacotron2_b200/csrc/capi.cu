@@ -29,6 +29,7 @@ size_t encoder_ws_bytes(int B, int T);
 int postnet_forward(T2Model* m, const T2PostnetArgs* a, cudaStream_t s);
 size_t postnet_ws_bytes(int B, int T);
 int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s);
+int mma_rate(int M, int N, int reps, int alternate_d, long long* out_host, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -338,6 +339,10 @@ int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host) {
   T2_CUDA(cudaDeviceSynchronize());
   T2_CUDA(cudaMemcpy(out_host, w.ctrl->prof, sizeof(long long) * 72, cudaMemcpyDeviceToHost));
   return T2_OK;
+}
+
+int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host) {
+  return mma_rate(M, N, reps, alternate_d, (long long*)out_host, 0);
 }
 
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes, float* C, void* stream) {
