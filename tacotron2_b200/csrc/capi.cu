@@ -94,11 +94,11 @@ int pack_model(T2Model* m, cudaStream_t s) {
     T2_CUDA(cudaMemsetAsync(m->zeros, 0, 8192 * 4, s));
   }
   // tensor-core conv / GEMM weight images
-  for (int i = 0; i < 3; ++i) T2_TRY(tc_pack_weights(m->w[W_ENC_CONV0 + 7 * i], kEnc, kEnc, kConvK, 256, &m->tc_enc_conv[i], s));
-  T2_TRY(tc_pack_weights(m->enc_lstm_wih, 8 * kEncH, kEnc, 1, 256, &m->tc_enc_wih, s));
+  for (int i = 0; i < 3; ++i) T2_TRY(tc_pack_weights(m->w[W_ENC_CONV0 + 7 * i], kEnc, kEnc, kConvK, 128, &m->tc_enc_conv[i], s));
+  T2_TRY(tc_pack_weights(m->enc_lstm_wih, 8 * kEncH, kEnc, 1, 128, &m->tc_enc_wih, s));
   for (int i = 0; i < 5; ++i) {
     const int ci = i == 0 ? kMel : kPost, co = i == 4 ? kMel : kPost;
-    T2_TRY(tc_pack_weights(m->w[W_POST_CONV0 + 7 * i], co, ci, kConvK, i == 4 ? 80 : 256, &m->tc_post_conv[i], s));
+    T2_TRY(tc_pack_weights(m->w[W_POST_CONV0 + 7 * i], co, ci, kConvK, i == 4 ? 80 : 128, &m->tc_post_conv[i], s));
   }
   T2_TRY(persistent_pack_create(m, s));
   return T2_OK;

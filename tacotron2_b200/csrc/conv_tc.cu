@@ -51,11 +51,11 @@ struct ConvParams {
   int cluster;
 };
 
-template <int NT, int WS>   // NT = output columns per CTA (MMA N), WS = weight stages
+template <int NT, int NH, int WS>   // NT = weight rows per stage (MMA N), NH = n-halves per CTA, WS = weight stages
 __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kWStage = NT * 64 * 2 * 2;   // hi + lo planes of NT rows x 64 k
-  constexpr int kTmem = NT <= 128 ? 128 : 256;
+  constexpr int kTmem = NT * NH <= 128 ? 128 : 256;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   uint8_t* s_w = smem;                                   // WS x kWStage (1024-aligned: SWIZZLE_128B)
@@ -93,10 +93,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
             const __half* src = p.in + (((long)(c * 8 + g) * 2 + hl) * p.in_plane_rows + (long)mrow * kTile) * 8;
             ptx::bulk_g2s_hint(s_a + sa * kAStage + (hl * 8 + g) * kSeg, src, kSeg, &a_full[sa], pol_a);
           }
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int th = 0; th < p.taps * NH; ++th) {
+          const int tap = th / NH, h = th - tap * NH;
           wait_bar(&w_empty[wst], wph ^ 1);
           ptx::mbar_arrive_expect_tx(&w_full[wst], kWStage);
-          const uint8_t* wsrc = p.wimg + (((size_t)nt * p.nchunks + c) * p.taps + tap) * kWStage;
+          const uint8_t* wsrc = p.wimg + (((size_t)(nt * NH + h) * p.nchunks + c) * p.taps + tap) * kWStage;
           if (cs == 1) {
             ptx::bulk_g2s_hint(s_w + wst * kWStage, wsrc, kWStage, &w_full[wst], pol_w);
           } else {
@@ -118,10 +119,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
         const int sa = c & 1;
         wait_bar(&a_full[sa], (c >> 1) & 1);
         const uint32_t ab = ptx::smem_u32(s_a + sa * kAStage);
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int th = 0; th < p.taps * NH; ++th) {
+          const int tap = th / NH, h = th - tap * NH;
           wait_bar(&w_full[wst], wph);
           ptx::tc_fence_after();
           const uint32_t wb = ptx::smem_u32(s_w + wst * kWStage);
+          const uint32_t dcol = tmem + h * NT;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t aoff = (2 * kk) * kSeg + (tap + tap0) * 16;
@@ -129,9 +132,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
             const uint64_t a_lo = ptx::make_smem_desc(ab + 8 * kSeg + aoff, kSeg, 128);
             const uint64_t b_hi = ptx::make_sw128_desc(wb + kk * 32);
             const uint64_t b_lo = ptx::make_sw128_desc(wb + NT * 128 + kk * 32);
-            ptx::umma_f16(tmem, a_hi, b_hi, idesc, (c | tap | kk) != 0 ? 1u : 0u);
-            ptx::umma_f16(tmem, a_lo, b_hi, idesc, 1u);
-            ptx::umma_f16(tmem, a_hi, b_lo, idesc, 1u);
+            ptx::umma_f16(dcol, a_hi, b_hi, idesc, (c | tap | kk) != 0 ? 1u : 0u);
+            ptx::umma_f16(dcol, a_lo, b_hi, idesc, 1u);
+            ptx::umma_f16(dcol, a_hi, b_lo, idesc, 1u);
           }
           if (cs == 1) ptx::umma_commit(&w_empty[wst]);
           else ptx::umma_commit_mc(&w_empty[wst], (uint16_t)((1u << cs) - 1u));
@@ -153,9 +156,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
     const int b = (int)(prow / span), pt = (int)(prow - (long)b * span) - p.seq_pad / 2;
     const bool valid = tile_live && b < p.B && pt >= 0 && pt < p.T;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    const int n0 = nt * NT;
+    const int n0 = nt * NT * NH;
     if (tile_live) {
-      for (int c0 = 0; c0 < NT; c0 += 8) {
+      for (int c0 = 0; c0 < NT * NH; c0 += 8) {
         float v[8];
         ptx::tmem_ld8(tl + c0, v);
         if (n0 + c0 >= p.cout) continue;
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
     // peers' multicast commits target our w_empty barriers: drain before leaving (producer thread state is
     // gone here, so wait on the parity each barrier reaches after its last use)
     if (tid == 0) {
-      const int total = p.nchunks * p.taps;
+      const int total = p.nchunks * p.taps * NH;
       for (int i = 0; i < WS; ++i) {
         const int uses = (total - i + WS - 1) / WS;       // number of times stage i was filled
         if (uses > 0) wait_bar(&w_empty[i], (uses - 1) & 1);
@@ -301,11 +304,11 @@ __global__ void fold_bn_bias_kernel(const float* cbias, const float* g, const fl
   shift[c] = b[c] + ((cbias ? cbias[c] : 0.f) - mean[c]) * s;
 }
 
-template <int NT, int WS>
+template <int NT, int NH, int WS>
 int launch_conv(const ConvParams& p, int n_tiles_n, cudaStream_t s) {
   constexpr int kWStage = NT * 64 * 2 * 2;
   const size_t smem = (size_t)WS * kWStage + 2 * kAStage + (5 + 2 * WS) * 8 + 64;
-  T2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  T2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, NH, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   const int gx = ((p.n_tiles_m + p.cluster - 1) / p.cluster) * p.cluster;
@@ -316,7 +319,7 @@ int launch_conv(const ConvParams& p, int n_tiles_n, cudaStream_t s) {
     at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, WS>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, NH, WS>, p);
   if (e != cudaSuccess) return fail(T2_ERR_CUDA, "conv_tc launch failed: %s", cudaGetErrorString(e));
   g_launch_count++;
   return T2_OK;
@@ -378,9 +381,9 @@ int tc_conv(const TcConvArgs& a, cudaStream_t s) {
   const char* e = getenv("T2_CONV_CLUSTER");
   p.cluster = e ? atoi(e) : 2;
   if (p.cluster != 1 && p.cluster != 2 && p.cluster != 4) p.cluster = 2;
-  if (a.nt_rows == 256) return launch_conv<256, 2>(p, (a.cout + 255) / 256, s);
-  if (a.nt_rows == 128) return launch_conv<128, 3>(p, (a.cout + 127) / 128, s);
-  if (a.nt_rows == 80) return launch_conv<80, 4>(p, (a.cout + 79) / 80, s);
+  // weights are packed in stages of nt_rows rows; a CTA covers 2 stages' worth of columns when cout allows
+  if (a.nt_rows == 128) return launch_conv<128, 2, 4>(p, (a.cout + 255) / 256, s);
+  if (a.nt_rows == 80) return launch_conv<80, 1, 4>(p, (a.cout + 79) / 80, s);
   return fail(T2_ERR_INVALID, "tc_conv: unsupported n-tile %d", a.nt_rows);
 }
 

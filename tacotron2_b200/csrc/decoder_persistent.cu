@@ -305,6 +305,24 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
   ptx::tc_fence_after();
 }
 
+// keep bits (bit i = element idx0+i is kept) of 8 consecutive dropout elements, Philox4x32-10 one block per 4
+__device__ __forceinline__ uint32_t philox_keep8(uint64_t seed, uint32_t site, uint64_t idx0, float pdrop) {
+  uint32_t bits = 0;
+  uint64_t blk_cur = ~0ull;
+  uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint64_t idx = idx0 + i, blk = idx >> 2;
+    if (blk != blk_cur) {
+      philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, 0x7ac07201u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+      blk_cur = blk;
+    }
+    const float u = (float)(o[idx & 3] >> 8) * (1.0f / 16777216.0f);
+    bits |= (u >= pdrop ? 1u : 0u) << i;
+  }
+  return bits;
+}
+
 // this lane's 8 accumulator columns of a consumer with n hi-columns at `base`: hi-part + lo-part, then
 // zero both (they are consumed)
 __device__ __forceinline__ void acc_take8(uint32_t t_lane, int base, int n, int col, float* s) {
@@ -376,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   float* s_q = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_xch = reinterpret_cast<float*>(sp); sp += kRows * kXchStride * 4;  // lo-row halves of the accumulators
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(sp); sp += kRows * 4;        // prenet keep bits of step t+1 (8 per row)
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
   float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128]
@@ -485,6 +504,31 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
+      // the otherwise idle lo-row lanes of column group 0 draw the prenet dropout bits this CTA will need
+      // at the END of this step (x1 columns on the projection CTAs, x2 columns on the prenet-2 CTAs)
+      if (p.infer && is_lo && cg == 0 && row < p.B && t + 1 < p.cap && (has_p || has_x2)) {
+        uint32_t bits = 0;
+        if (has_x2) {
+          const int col0 = (cta - kX2Cta0) * 8;
+          if (p.prenet_keep) {
+            const uint8_t* kp = p.prenet_keep + ((long)(t + 1) * 2 + 1) * p.B * kPre + (long)row * kPre + col0;
+            for (int j = 0; j < 8; ++j) bits |= (kp[j] != 0 ? 1u : 0u) << j;
+          } else {
+            bits = philox_keep8(p.seed, (t + 1) * 4 + 1, (uint64_t)row * kPre + col0, 0.5f);
+          }
+        } else {
+          const int pc0 = (cta - kPCta0) * 8;
+          for (int j = 0; j < 8; ++j) {
+            const int col = pc0 + j - (kMel + 1);
+            if (col < 0 || col >= kPre) continue;
+            const long idx = (long)row * kPre + col;
+            const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
+                                            : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
+            bits |= (keep ? 1u : 0u) << j;
+          }
+        }
+        s_mask[row] = bits;
+      }
       T2_PROF(1);
       grid_barrier(ctrl, bar_target);                                          // B1: ah_t complete
       T2_PROF(2);
@@ -518,11 +562,29 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
       for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
       uint8_t* aimg = rg.stage0;
+      const int smem_rows = min(T, (kStages * kStageBytes) / (kEnc / 2 * 4));   // memory rows staged in the ring
       for (int t0 = 0; t0 < ntiles; t0 += 2) {            // rounds of up to 2 tiles of 128 positions
         const int nt = min(2, ntiles - t0);
         const int j_end = min(T, (t0 + nt) * 128);
+        int nact = 0;
+        for (int tl = 0; tl < nt; ++tl)
+          if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
+        // processed-memory rows of this warp's first 4 chunks: issued now, consumed after the MMAs
+        float4 pf[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = cg + u * (kWarps / 4);
+          const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
+          if (c < nact * 16 && j < T) {
+            const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
+            pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
+            pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+          } else {
+            pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
-        //     canonical tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
+        //     SWIZZLE_128B tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
         //     accumulator rows are never read                                        model.py:23
         for (int item = t0 * 128 * 8 + tid; item < j_end * 8; item += kThreads) {
           const int j = item >> 3, g8 = item & 7;
@@ -571,26 +633,35 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         rg.acc_phase ^= 1;
         ptx::tc_fence_after();
         T2_PROF(16);
+        if (t0 + 2 >= ntiles) {
+          // the ring is idle until the next event: stage this CTA's half of the encoder memory rows in it
+          // with cp.async while the energies / softmax run (consumed by the context product below)
+          const uint32_t sbase = ptx::smem_u32(rg.stage0);
+          const float* msrc = p.memory + (long)b * T * kEnc + ahalf * (kEnc / 2);
+          for (int i = tid; i < smem_rows * (kEnc / 2 / 4); i += kThreads) {
+            const int j = i >> 6, c4 = i & 63;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)i * 16u),
+                         "l"(msrc + (long)j * kEnc + c4 * 4)
+                         : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
         //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
         {
-          int nact = 0;
-          for (int tl = 0; tl < nt; ++tl)
-            if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
           float part = 0.f;
           int cur_tile = -1;
           for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
-            float4 pf[4][2];      // processed-memory rows, prefetched 4 chunks at a time
+            if (c0 != cg) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int c = c0 + u * (kWarps / 4);
-              const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
-              if (c < nact * 16 && j < T) {
-                const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
-                pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
-                pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-              } else {
-                pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * (kWarps / 4);
+                const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
+                if (c < nact * 16 && j < T) {
+                  const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
+                  pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
+                  pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+                }
               }
             }
 #pragma unroll
@@ -618,49 +689,45 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         __syncthreads();
         T2_PROF(17);
       }
+      // mask + softmax (model.py:79-82): every warp reduces all T energies itself (shuffles only, no
+      // cross-warp exchange), then the threads split the normalised write-out
       const int len = p.mem_len ? p.mem_len[b] : T;
-      float mx = -INFINITY;                                     // mask + softmax         model.py:79-82
-      for (int j = tid; j < T; j += kThreads) {
-        const float e = (j < len) ? s_e[j] : p.score_mask_value;
-        s_e[j] = e;
-        mx = fmaxf(mx, e);
-      }
+      float mx = -INFINITY;
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, (j < len) ? s_e[j] : p.score_mask_value);
       mx = warp_max_f(mx);
-      if (lane == 0) s_red[warp] = mx;
-      __syncthreads();
-      mx = s_red[0];
-#pragma unroll
-      for (int w = 1; w < kWarps; ++w) mx = fmaxf(mx, s_red[w]);
-      __syncthreads();
       float sum = 0.f;
-      for (int j = tid; j < T; j += kThreads) { const float e = expf(s_e[j] - mx); s_e[j] = e; sum += e; }
+      for (int j = lane; j < T; j += 32) sum += expf(((j < len) ? s_e[j] : p.score_mask_value) - mx);
       sum = warp_sum_f(sum);
-      if (lane == 0) s_red[warp] = sum;
-      __syncthreads();
-      sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) sum += s_red[w];
       const float inv = 1.f / sum;
+      __syncthreads();                                           // all warps have read the raw energies
       for (int j = tid; j < T; j += kThreads) {
-        const float a = s_e[j] * inv;
+        const float a = expf(((j < len) ? s_e[j] : p.score_mask_value) - mx) * inv;
         s_e[j] = a;
         s_pad0[halfk + j] = a;                                                // becomes "previous"
         s_pad1[halfk + j] += a;                                               // model.py:365
         if (ahalf == 0) p.align[((long)b * p.cap + t) * T + j] = a;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
       T2_PROF(18);
       {                                                           // context = aw . memory  model.py:83-84
-        float* scr = reinterpret_cast<float*>(rg.stage0);         // [8][256] partial sums (ring is idle)
         const int c4 = tid & 63, jg = tid >> 6;                   // 64 float4 = this CTA's 256 columns; 8 j-groups
-        const float* mp = p.memory + (long)b * T * kEnc + ahalf * (kEnc / 2) + c4 * 4;
+        const float4* ms = reinterpret_cast<const float4*>(rg.stage0);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 10
-        for (int j = jg; j < T; j += 8) {
+#pragma unroll 4
+        for (int j = jg; j < smem_rows; j += 8) {
+          const float4 m = ms[j * 64 + c4];
+          const float a = s_e[j];
+          acc.x = fmaf(a, m.x, acc.x); acc.y = fmaf(a, m.y, acc.y); acc.z = fmaf(a, m.z, acc.z); acc.w = fmaf(a, m.w, acc.w);
+        }
+        const float* mp = p.memory + (long)b * T * kEnc + ahalf * (kEnc / 2) + c4 * 4;
+        for (int j = smem_rows + jg; j < T; j += 8) {             // rows that did not fit in the ring
           const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (long)j * kEnc));
           const float a = s_e[j];
           acc.x = fmaf(a, m.x, acc.x); acc.y = fmaf(a, m.y, acc.y); acc.z = fmaf(a, m.z, acc.z); acc.w = fmaf(a, m.w, acc.w);
         }
+        __syncthreads();                                          // everyone is done reading the staged rows
+        float* scr = reinterpret_cast<float*>(rg.stage0);         // [8][256] partial sums
         *reinterpret_cast<float4*>(scr + jg * (kEnc / 2) + c4 * 4) = acc;
         __syncthreads();
         if (tid < kEnc / 4) {
@@ -741,12 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
             const int col = pc - (kMel + 1);
             float r = fmaxf(v, 0.f);
-            if (p.infer && t + 1 < p.cap) {
-              const long idx = (long)row * kPre + col;
-              const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
-                                              : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
-              r = keep ? r * 2.f : 0.f;
-            }
+            if (p.infer && t + 1 < p.cap) r = ((s_mask[row] >> j) & 1u) ? r * 2.f : 0.f;
             if (p.infer) {
               __half h, l;
               split_fp16(r, h, l);
@@ -788,12 +850,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           const int col0 = (cta - kX2Cta0) * 8;
           float r[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long idx = (long)row * kPre + col0 + j;
-            const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 1) * p.B * kPre + idx] != 0
-                                            : philox_keep(p.seed, (t + 1) * 4 + 1, idx, 0.5f);
-            r[j] = keep ? fmaxf(g[j] + s_xch[row * kXchStride + j], 0.f) * 2.f : 0.f;
-          }
+          const uint32_t bits = s_mask[row];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            r[j] = ((bits >> j) & 1u) ? fmaxf(g[j] + s_xch[row * kXchStride + j], 0.f) * 2.f : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; j += 2) store_split2(p.x2_img, row, col0 + j, r[j], r[j + 1]);
         }
@@ -836,7 +896,7 @@ static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
   return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
-         (size_t)kRows * kXchStride * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
+         (size_t)kRows * kXchStride * 4 + kRows * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
 }
 
 size_t persistent_ws_bytes(int B, int T) {

@@ -340,14 +340,14 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
       const int wb = W_ENC_CONV0 + 7 * i;
       T2_TRY(tc_fold_bn(m->w[wb + 1], m->w[wb + 2], m->w[wb + 3], m->w[wb + 4], m->w[wb + 5], m->cfg.bn_eps, scale, shift, kEnc, s));
       TcConvArgs c; memset(&c, 0, sizeof(c));
-      c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_conv[i]; c.taps = kConvK; c.B = B; c.T = T; c.cout = kEnc; c.nt_rows = 256;
+      c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_conv[i]; c.taps = kConvK; c.B = B; c.T = T; c.cout = kEnc; c.nt_rows = 128;
       c.scale = scale; c.shift = shift; c.act = 1; c.out_mode = 0; c.out_planes = nxt;
       T2_TRY(tc_conv(c, s));
       __half* tmp = cur; cur = nxt; nxt = tmp;
     }
     T2_TRY(tc_fold_bn(m->enc_lstm_b, nullptr, nullptr, nullptr, nullptr, 0.f, scale, shift, 8 * kEncH, s));
     TcConvArgs c; memset(&c, 0, sizeof(c));
-    c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_wih; c.taps = 1; c.B = B; c.T = T; c.cout = 8 * kEncH; c.nt_rows = 256;
+    c.in = cur; c.cin_pad = kEnc; c.wimg = m->tc_enc_wih; c.taps = 1; c.B = B; c.T = T; c.cout = 8 * kEncH; c.nt_rows = 128;
     c.scale = scale; c.shift = shift; c.act = 0; c.out_mode = 1; c.out_f32 = gin; c.ldo = 8 * kEncH;
     T2_TRY(tc_conv(c, s));
   } else {
@@ -430,7 +430,7 @@ int postnet_forward(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
       T2_TRY(tc_fold_bn(m->w[wb + 1], m->w[wb + 2], m->w[wb + 3], m->w[wb + 4], m->w[wb + 5], m->cfg.bn_eps, scale, shift, cout, s));
       TcConvArgs c; memset(&c, 0, sizeof(c));
       c.in = cur; c.cin_pad = i == 0 ? 128 : kPost; c.wimg = m->tc_post_conv[i]; c.taps = kConvK; c.B = B; c.T = T;
-      c.cout = cout; c.nt_rows = i == 4 ? 80 : 256; c.scale = scale; c.shift = shift; c.act = i == 4 ? 0 : 2;
+      c.cout = cout; c.nt_rows = i == 4 ? 80 : 128; c.scale = scale; c.shift = shift; c.act = i == 4 ? 0 : 2;
       if (i < 4) { c.out_mode = 0; c.out_planes = nxt; }
       else { c.out_mode = 2; c.out_f32 = a->mel_post; c.residual = a->add_residual ? a->mel : nullptr; c.res_batch_stride = bs; c.row_len = a->lengths; }
       T2_TRY(tc_conv(c, s));
