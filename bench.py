@@ -78,38 +78,67 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def _best_threads(fn, candidates):
+    """Runs fn() under each thread count and returns (best_seconds, best_threads)."""
+    best = None
+    for th in candidates:
+        torch.set_num_threads(th)
+        fn()                                  # warm-up at this thread count
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, th)
+    return best
+
+
 def cpu_port_sample(threads, dec_steps=60):
-    """Times the oracle port on the host cores on a bounded sample of the SAME workload:
-    encoder + `dec_steps` of the 800 decoder steps + postnet at B=64, T_text=150; the decoder part is
-    extrapolated linearly to 800 steps (every step does identical work)."""
+    """Times the oracle port (the reference's algorithm in plain torch CPU ops) on the host cores on a
+    bounded sample of the SAME workload: encoder + `dec_steps` of the 800 decoder steps + postnet at B=64,
+    T_text=150; the decoder part is extrapolated linearly to 800 steps (every step does identical work).
+    Each component runs at the thread count (<= all host threads) that is fastest for it -- small
+    recurrent GEMMs are slower with 100+ threads than with 16."""
     from oracle import tacotron2_oracle as O
     from tests.common import keep_mask, rand_text
-    torch.set_num_threads(threads)
+    cands = sorted({t for t in (8, 16, 32, 64, threads) if t <= threads})
     sd = synth_weights()
     text = rand_text(B_PER_GPU, T_TEXT, 1)
     keep = keep_mask((dec_steps + 3, 2, B_PER_GPU, 256), 0.5, 2)
     with torch.no_grad():
+        emb = sd["embedding.weight"][text].transpose(1, 2)
+        # encoder: tune on a 1/5 slice of the sequence, then time the full one
+        _, th_enc = _best_threads(lambda: O.encoder(sd, emb[:, :, :30]), cands)
+        torch.set_num_threads(th_enc)
         t0 = time.perf_counter()
-        memory = O.encoder(sd, sd["embedding.weight"][text].transpose(1, 2))
+        memory = O.encoder(sd, emb)
         t_enc = time.perf_counter() - t0
-        st = O.init_decoder_state(sd, memory)
-        x = memory.new_zeros(B_PER_GPU, 80)
-        times = []
-        for t in range(dec_steps + 3):
-            t0 = time.perf_counter()
-            px = O.prenet(sd, x, keep[t, 0], keep[t, 1])
-            x, _, _ = O.decode_step(sd, st, memory, px)
-            times.append(time.perf_counter() - t0)
-        times = sorted(times[3:])
+        st0 = O.init_decoder_state(sd, memory)
+
+        def steps(n, st=None):
+            st = st or {k: v.clone() for k, v in st0.items()}
+            x = memory.new_zeros(B_PER_GPU, 80)
+            ts = []
+            for t in range(n):
+                t0 = time.perf_counter()
+                px = O.prenet(sd, x, keep[t, 0], keep[t, 1])
+                x, _, _ = O.decode_step(sd, st, memory, px)
+                ts.append(time.perf_counter() - t0)
+            return ts
+        _, th_dec = _best_threads(lambda: steps(6), cands)
+        torch.set_num_threads(th_dec)
+        times = sorted(steps(dec_steps + 3)[3:])
         step = times[len(times) // 2]
         mel = torch.randn(B_PER_GPU, 80, T_MEL)
+        _, th_post = _best_threads(lambda: O.postnet(sd, mel[:, :, :100]), cands)
+        torch.set_num_threads(th_post)
         t0 = time.perf_counter()
         O.postnet(sd, mel)
         t_post = time.perf_counter() - t0
     total = t_enc + T_MEL * step + t_post
     return {"value": B_PER_GPU * T_MEL / total, "unit": "mel frames/s", "cores": threads, "kind": "port",
-            "sample": "oracle port, B=64 T_text=150: encoder (%.3f s) + median of %d decoder steps (%.1f us/step, "
-                      "x800) + postnet T_mel=800 (%.3f s)" % (t_enc, dec_steps, step * 1e6, t_post),
+            "sample": "oracle port, B=64 T_text=150, fp32, %d host threads available: encoder %.3f s (%d thr) + median of "
+                      "%d decoder steps %.1f us/step x800 (%d thr) + postnet T_mel=800 %.3f s (%d thr)"
+                      % (threads, t_enc, th_enc, dec_steps, step * 1e6, th_dec, t_post, th_post),
             "decoder_step_us": step * 1e6}, total
 
 

@@ -106,7 +106,6 @@ int pack_model(T2Model* m, cudaStream_t s) {
 
 // ---- decoder workspace --------------------------------------------------------------------------
 size_t decoder_ws_bytes(int B, int T, int cap) {
-  (void)cap;
   size_t n = 0;
   n += align256((size_t)B * T * kAtt * 4);                                   // pm
   n += align256(((size_t)B * (2 * kARnn + 2 * kDRnn + kEnc) + 2 * (size_t)B * T) * 4);  // state
@@ -114,7 +113,7 @@ size_t decoder_ws_bytes(int B, int T, int cap) {
   n += align256((size_t)B * 4 * kARnn * 4);                                  // gates
   n += align256((size_t)B * (kMel + 1) * 4);                                 // proj
   n += align256(sizeof(DecoderCtrl));
-  n += align256(persistent_ws_bytes(B, T));
+  n += align256(persistent_ws_bytes(B, T, cap));
   return n + 256;
 }
 
@@ -139,7 +138,7 @@ int decoder_ws_carve(const T2DecoderArgs* a, DecoderWs* w) {
   w->gates = (float*)p; p += align256((size_t)B * 4 * kARnn * 4);
   w->proj = (float*)p; p += align256((size_t)B * (kMel + 1) * 4);
   w->ctrl = (DecoderCtrl*)p; p += align256(sizeof(DecoderCtrl));
-  w->persistent = p; w->persistent_bytes = persistent_ws_bytes(B, T);
+  w->persistent = p; w->persistent_bytes = persistent_ws_bytes(B, T, a->n_steps_cap);
   return T2_OK;
 }
 

@@ -31,7 +31,7 @@ struct DecoderWs {
 };
 
 size_t decoder_ws_bytes(int B, int T, int cap);
-size_t persistent_ws_bytes(int B, int T);
+size_t persistent_ws_bytes(int B, int T, int cap);
 int decoder_ws_carve(const T2DecoderArgs* a, DecoderWs* w);
 int decoder_run_stepwise(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);
 int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);

@@ -899,17 +899,18 @@ static size_t persistent_smem_bytes(int T) {
          (size_t)kRows * kXchStride * 4 + kRows * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
 }
 
-size_t persistent_ws_bytes(int B, int T) {
+size_t persistent_ws_bytes(int B, int T, int cap) {
   (void)B; (void)T;
   // activation images: x2 (4 chunks), ah (16), ctx (8), dh (16), x1 (4)  + q (64 x 128 fp32)
-  return (size_t)(4 + 16 + 8 + 16 + 4) * kXChunkBytes + (size_t)kRows * kAtt * 4 + 1024;
+  // + (teacher forcing) the x2 images of every step: cap x 4 chunks
+  return (size_t)(4 + 16 + 8 + 16 + 4) * kXChunkBytes + (size_t)kRows * kAtt * 4 + 1024 +
+         (size_t)cap * 4 * kXChunkBytes;
 }
 
 bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
   if (!m->pk) return false;
   if (m->sm_count < kG) return false;
   if (a->B > kRows) return false;
-  if (a->mode != T2_MODE_INFER) return false;   // teacher forcing runs on the stepwise path for now
   if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
   return true;
 }
@@ -1016,7 +1017,7 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   DecoderWs w;
   T2_TRY(decoder_ws_carve(a, &w));
   T2_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(DecoderCtrl), s));
-  T2_CUDA(cudaMemsetAsync(w.persistent, 0, w.persistent_bytes, s));          // zero images (model.py:258-284)
+  T2_CUDA(cudaMemsetAsync(w.persistent, 0, (size_t)(4 + 16 + 8 + 16 + 4) * kXChunkBytes + (size_t)kRows * kAtt * 4, s));  // zero images (model.py:258-284)
   {  // processed_memory = memory_layer(memory)                                  (model.py:288)
     GemmArgs g;
     g.seg[0] = {a->memory, kEnc, m->w[W_ATT_MEMORY], kEnc, kEnc};
@@ -1046,7 +1047,14 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   p.gate_threshold = a->gate_threshold; p.score_mask_value = a->score_mask_value;
   p.p_att = m->cfg.p_attention_dropout; p.p_dec = m->cfg.p_decoder_dropout; p.seed = a->seed;
   if (!p.infer) {
-    return fail(T2_ERR_UNSUPPORTED, "persistent decoder: teacher-forced mode needs the x2 image pre-pass (not wired)");
+    // teacher forcing (model.py:396-405): the prenet outputs of all steps are known up front -> convert
+    // them once into x2 operand images, the kernel then skips the prenet events and their two barriers
+    uint8_t* timg = (uint8_t*)p.q + (size_t)kRows * kAtt * 4;
+    timg = (uint8_t*)(((uintptr_t)timg + 1023) & ~(uintptr_t)1023);
+    rows_to_image_kernel<<<dim3(4, cap), 256, 0, s>>>(a->teacher_prenet, kPre, B, kPre, (long)B * kPre, timg,
+                                                      (long)4 * kXChunkBytes);
+    T2_LAUNCH_CHECK();
+    p.teacher_x2_img = timg;
   }
   const size_t smem = persistent_smem_bytes(T);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -75,11 +75,12 @@ def test_inference_matches_reference_golden(name, impl, impl_name):
     assert torch.equal(dec_e, dec_g)
 
 
+@pytest.mark.parametrize("impl,impl_name", IMPLS)
 @pytest.mark.parametrize("name,training", [("forward_eval_b4", False), ("forward_train_b4", True)])
-def test_teacher_forced_forward_matches_reference_golden(name, training):
+def test_teacher_forced_forward_matches_reference_golden(name, training, impl, impl_name):
     g = load(name)
     sd, text, tl, ol, mels, m = forward_inputs(g)
-    model = make_model(sd, training=training)
+    model = make_model(sd, impl=impl, training=training)
     post_keep = [m["qk4"][i] for i in range(4)] + [m["qk1"]]
     with torch.no_grad(), t2.dropout_masks(prenet=m["pk"], att=m["ak"], dec=m["dk"], enc=m["ek"], post=post_keep):
         out = model((text.cuda(), tl.cuda(), mels.cuda(), int(tl.max()), ol.cuda()))
