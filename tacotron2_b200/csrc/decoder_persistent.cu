@@ -204,8 +204,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Decode
 // grid-wide barrier: one monotonically increasing arrival counter; arrive = red.release, wait = poll with
 // ld.acquire until the counter reaches this barrier's target (no reset / generation hop).  Also orders
 // the generic-proxy stores of the epilogues before the async-proxy (bulk copy) reads of the next event.
-__device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& target) {
+__device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& target, uint32_t cs, uint32_t rank) {
   ptx::fence_proxy_async();
+  if (cs > 1) {
+    // hierarchical: hardware cluster barrier, one global arrival + one poller per cluster, cluster barrier
+    // again to release the other ranks (16-32 global participants instead of 128)
+    __threadfence();
+    ptx::cluster_sync_all();
+    target += gridDim.x / cs;
+    if (rank == 0 && threadIdx.x == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
+      const unsigned long long t0 = clock64();
+      while (true) {
+        unsigned int c;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->bar_count) : "memory");
+        if ((int)(c - target) >= 0) break;
+        if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 100);
+      }
+      __threadfence();
+    }
+    ptx::cluster_sync_all();
+    ptx::fence_proxy_async();
+    return;
+  }
   __syncthreads();
   target += gridDim.x;
   if (threadIdx.x == 0) {
@@ -248,22 +269,46 @@ struct Ring {
   uint32_t acc_phase;          // all threads
   uint64_t pol_x, pol_w;       // L2 eviction policies of the activation / weight streams
   uint32_t cs, rank;           // cluster size (1 = no multicast) and this CTA's rank in it
+  uint32_t pre;                // stages whose weight chunk was already issued for the upcoming event
 };
+
+// Weight chunks do not depend on the grid barrier that separates two events (only the activation does):
+// the producer arms the first kStages stages of the NEXT event and issues their weight copies right after
+// the current event's last chunk, so their L2 / HBM latency overlaps the epilogue and the barrier.
+__device__ __forceinline__ void prefetch_weights(Ring& rg, const EventPlan& nx, const uint8_t* w_img,
+                                                 DecoderCtrl* ctrl) {
+  uint32_t s = rg.p_stage, ph = rg.p_phase;
+  for (int i = 0; i < kStages; ++i) {
+    mbar_wait(&rg.empty[s], ph ^ 1, ctrl, 205);
+    ptx::mbar_arrive_expect_tx(&rg.full[s], kXChunkBytes + nx.w_bytes);
+    ptx::bulk_g2s_hint(rg.stage(s) + kXChunkBytes, w_img + nx.w_off + (size_t)i * nx.w_bytes, nx.w_bytes,
+                       &rg.full[s], rg.pol_w);
+    if (++s == kStages) { s = 0; ph ^= 1; }
+  }
+  rg.pre = kStages;
+}
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight rows through the ring
 // and issues the MMAs (1 per 16-wide K step).  Called by all threads; returns after the accumulators are
 // complete.  Every MMA accumulates (the epilogues zero what they consume).
 __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
                                           const uint8_t* w_img, int chunks, uint32_t tmem_base,
-                                          DecoderCtrl* ctrl) {
+                                          DecoderCtrl* ctrl, const EventPlan* next) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (ep.nrows == 0) return;           // this CTA (and its whole cluster) has no consumer of this activation
+  if (ep.nrows == 0) {                 // this CTA (and its whole cluster) has no consumer of this activation
+    if (threadIdx.x == 0 && next != nullptr && next->nrows != 0 && rg.pre == 0) prefetch_weights(rg, *next, w_img, ctrl);
+    return;
+  }
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < chunks; ++i) {
-        mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
         uint8_t* st = rg.stage(rg.p_stage);
-        ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
+        if ((uint32_t)i >= rg.pre) {     // not armed / issued ahead of time
+          mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
+          ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
+          ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
+                             &rg.full[rg.p_stage], rg.pol_w);
+        }
         if (rg.cs == 1) {
           ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
         } else {   // every CTA of the cluster fetches 1/cs of the activation chunk and multicasts it to all
@@ -271,10 +316,10 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
           ptx::bulk_g2s_mc_hint(st + rg.rank * slice, x_img + (size_t)i * kXChunkBytes + rg.rank * slice, slice,
                                 &rg.full[rg.p_stage], (uint16_t)((1u << rg.cs) - 1u), rg.pol_x);
         }
-        ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
-                           &rg.full[rg.p_stage], rg.pol_w);
         if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
       }
+      rg.pre = 0;
+      if (next != nullptr && next->nrows != 0) prefetch_weights(rg, *next, w_img, ctrl);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -351,7 +396,7 @@ struct KParams {
   float* q;                         // (64, 128) fp32
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   DecoderCtrl* ctrl;
-  int B, T, cap, infer, training, cluster;
+  int B, T, cap, infer, training, cluster, hier_barrier;
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
 };
@@ -401,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
+  rg.pre = 0;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
@@ -429,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   const CtaPlan& plan = p.plans[cta];
   DecoderCtrl* ctrl = p.ctrl;
   unsigned int bar_target = 0;
+  const uint32_t bar_cs = p.hier_barrier ? rg.cs : 1;
   // epilogue role of this thread: TMEM lane quadrant quad = warp % 4 (hardware rule), column group
   // cg = warp / 4.  Accumulator lane = MMA row: lanes 0-63 are the X_hi rows (batch rows), lanes 64-127
   // the X_lo rows of the same batch rows; quadrants 2/3 hand their partial sums to quadrants 0/1.
@@ -478,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     // ======== E0: x2_t -> attention LSTM gates, epilogue -> ah_t ==================== model.py:352-356
     {
       const uint8_t* x2 = p.infer ? p.x2_img : p.teacher_x2_img + (size_t)t * 4 * kXChunkBytes;
-      run_event(rg, plan.ev[0], x2, p.wimg, 4, tmem_base, ctrl);
+      run_event(rg, plan.ev[0], x2, p.wimg, 4, tmem_base, ctrl, &plan.ev[1]);
       T2_PROF(0);
       float g[8];
       T2_TAKE_GATES(kColA, kNA, g);
@@ -530,12 +577,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         s_mask[row] = bits;
       }
       T2_PROF(1);
-      grid_barrier(ctrl, bar_target);                                          // B1: ah_t complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B1: ah_t complete
       T2_PROF(2);
     }
     // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
     {
-      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl);
+      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr);   // the attention phase reuses the ring as scratch
       if (has_q) {
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
@@ -551,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       T2_PROF(3);
-      grid_barrier(ctrl, bar_target);                                          // B2: q complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B2: q complete
       T2_PROF(4);
     }
     // ======== attention for batch row (cta mod 64) ============================ model.py:43-86, 358-365
@@ -741,11 +788,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       T2_PROF(19);
     }
     T2_PROF(5);
-    grid_barrier(ctrl, bar_target);                                            // B3: ctx_t complete
+    grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                            // B3: ctx_t complete
     T2_PROF(6);
     // ======== E2: ctx_t -> dec gates (rest), next att gates, projection (part); epilogue -> dh_t
     {
-      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, tmem_base, ctrl);
+      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, tmem_base, ctrl, &plan.ev[3]);
       T2_PROF(7);
       float g[8];
       T2_TAKE_GATES(kColD, kND, g);
@@ -772,12 +819,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         store_split2(p.dh_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
       T2_PROF(8);
-      grid_barrier(ctrl, bar_target);                                          // B4: dh_t complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B4: dh_t complete
       T2_PROF(9);
     }
     // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
     {
-      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl);
+      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl,
+                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr);   // INFER: the loop may end after this step
       T2_PROF(10);
       if (tid == 0) *s_live = 0;
       float g[8];
@@ -828,7 +876,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       }
       T2_PROF(11);
       if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
-      grid_barrier(ctrl, bar_target);                                          // B5: x1 / stop flag complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B5: x1 / stop flag complete
       T2_PROF(12);
       int all_done;
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
@@ -836,7 +884,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     }
     // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
     {
-      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl);
+      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0]);   // step t+1 is certain here
       if (has_x2) {
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
@@ -859,7 +907,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       T2_PROF(13);
-      grid_barrier(ctrl, bar_target);                                          // B6: x2_(t+1) complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B6: x2_(t+1) complete
       T2_PROF(14);
     }
   }
@@ -1065,6 +1113,10 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
     if (e) want = atoi(e);
     if (want != 1 && want != 2 && want != 4 && want != 8) want = 8;
   }
+  {
+    const char* e = getenv("T2_HIER_BARRIER");   // 0 = flat 128-way barrier
+    p.hier_barrier = e ? atoi(e) : 1;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1095,6 +1147,8 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
     le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
   }
   if (le != cudaSuccess) return fail(T2_ERR_CUDA, "persistent decoder launch failed: %s", cudaGetErrorString(le));
+  if (getenv("T2_VERBOSE")) fprintf(stderr, "[t2b200] persistent decoder: B=%d T_enc=%d cap=%d cluster=%d hier_barrier=%d smem=%zu\n",
+                                    B, T, cap, p.cluster, p.hier_barrier, smem);
   g_launch_count++;
   return T2_OK;
 }
@@ -1118,7 +1172,7 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = rg.pol_w = ptx::policy_evict_last();
-  rg.cs = 1; rg.rank = 0;
+  rg.cs = 1; rg.rank = 0; rg.pre = 0;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);
@@ -1135,10 +1189,10 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   ptx::tmem_wait_st();
   ptx::tc_fence_before();
   __syncthreads();
-  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl);
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl, &ep);      // second pass uses the prefetched weights
   ptx::tc_fence_before();
   __syncthreads();
-  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl);
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl, nullptr);
   const int row = (quad & 1) * 32 + lane;
   float g[kHiCols / 8][8];
   for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
