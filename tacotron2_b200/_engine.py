@@ -214,9 +214,11 @@ class Engine:
         memory = memory.to(device=self.device, dtype=torch.float32).contiguous()
         B, T = int(memory.shape[0]), int(memory.shape[1])
         cap = int(n_steps_cap)
-        mel = torch.empty(B, cap, self.hp.n_mel_channels, device=self.device, dtype=torch.float32)
-        gate = torch.empty(B, cap, device=self.device, dtype=torch.float32)
-        align = torch.empty(B, cap, T, device=self.device, dtype=torch.float32)
+        # zero-initialised: batches of more than 64 rows run as independent 64-row launches that may stop at
+        # different steps; frames past a launch's last step stay zero
+        mel = torch.zeros(B, cap, self.hp.n_mel_channels, device=self.device, dtype=torch.float32)
+        gate = torch.zeros(B, cap, device=self.device, dtype=torch.float32)
+        align = torch.zeros(B, cap, T, device=self.device, dtype=torch.float32)
         mel_lengths = torch.zeros(B, device=self.device, dtype=torch.int32)
         n_steps = torch.zeros(1, device=self.device, dtype=torch.int32)
         ws = self._workspace("dec", L.t2_decoder_workspace_bytes(self.handle, B, T, cap))

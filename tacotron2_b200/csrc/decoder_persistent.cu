@@ -397,6 +397,7 @@ struct KParams {
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   DecoderCtrl* ctrl;
   int B, T, cap, infer, training, cluster, hier_barrier;
+  int b0, Btot;                     // this launch handles batch rows [b0, b0 + B) of Btot (dropout mask / Philox indexing)
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
 };
@@ -542,8 +543,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           float h = go * tanh_fast(c_att[u]);
           if (p.training) {
             const int unit = cta * 8 + cg * 2 + u;
-            const long idx = (long)row * kARnn + unit;
-            const bool keep = p.att_keep ? p.att_keep[(long)t * p.B * kARnn + idx] != 0
+            const long idx = (long)(p.b0 + row) * kARnn + unit;
+            const bool keep = p.att_keep ? p.att_keep[(long)t * p.Btot * kARnn + idx] != 0
                                          : philox_keep(p.seed, t * 4 + 2, idx, p.p_att);
             h = keep ? h * (1.f / (1.f - p.p_att)) : 0.f;
           }
@@ -558,18 +559,18 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (has_x2) {
           const int col0 = (cta - kX2Cta0) * 8;
           if (p.prenet_keep) {
-            const uint8_t* kp = p.prenet_keep + ((long)(t + 1) * 2 + 1) * p.B * kPre + (long)row * kPre + col0;
+            const uint8_t* kp = p.prenet_keep + ((long)(t + 1) * 2 + 1) * p.Btot * kPre + (long)(p.b0 + row) * kPre + col0;
             for (int j = 0; j < 8; ++j) bits |= (kp[j] != 0 ? 1u : 0u) << j;
           } else {
-            bits = philox_keep8(p.seed, (t + 1) * 4 + 1, (uint64_t)row * kPre + col0, 0.5f);
+            bits = philox_keep8(p.seed, (t + 1) * 4 + 1, (uint64_t)(p.b0 + row) * kPre + col0, 0.5f);
           }
         } else {
           const int pc0 = (cta - kPCta0) * 8;
           for (int j = 0; j < 8; ++j) {
             const int col = pc0 + j - (kMel + 1);
             if (col < 0 || col >= kPre) continue;
-            const long idx = (long)row * kPre + col;
-            const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.B * kPre + idx] != 0
+            const long idx = (long)(p.b0 + row) * kPre + col;
+            const bool keep = p.prenet_keep ? p.prenet_keep[((long)(t + 1) * 2 + 0) * p.Btot * kPre + idx] != 0
                                             : philox_keep(p.seed, (t + 1) * 4 + 0, idx, 0.5f);
             bits |= (keep ? 1u : 0u) << j;
           }
@@ -616,20 +617,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         int nact = 0;
         for (int tl = 0; tl < nt; ++tl)
           if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
-        // processed-memory rows of this warp's first 4 chunks: issued now, consumed after the MMAs
-        float4 pf[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = cg + u * (kWarps / 4);
-          const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
-          if (c < nact * 16 && j < T) {
-            const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
-            pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
-            pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-          } else {
-            pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
         // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
         //     SWIZZLE_128B tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
         //     accumulator rows are never read                                        model.py:23
@@ -699,16 +686,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           float part = 0.f;
           int cur_tile = -1;
           for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
-            if (c0 != cg) {
+            float4 pf[4][2];      // processed-memory rows, fetched 4 chunks at a time
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int c = c0 + u * (kWarps / 4);
-                const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
-                if (c < nact * 16 && j < T) {
-                  const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
-                  pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
-                  pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-                }
+            for (int u = 0; u < 4; ++u) {
+              const int c = c0 + u * (kWarps / 4);
+              const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
+              if (c < nact * 16 && j < T) {
+                const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
+                pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
+                pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
+              } else {
+                pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
 #pragma unroll
@@ -809,8 +797,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
           float h = go * tanh_fast(c_dec[u]);
           if (p.training) {
             const int unit = cta * 8 + cg * 2 + u;
-            const long idx = (long)row * kDRnn + unit;
-            const bool keep = p.dec_keep ? p.dec_keep[(long)t * p.B * kDRnn + idx] != 0
+            const long idx = (long)(p.b0 + row) * kDRnn + unit;
+            const bool keep = p.dec_keep ? p.dec_keep[(long)t * p.Btot * kDRnn + idx] != 0
                                          : philox_keep(p.seed, t * 4 + 3, idx, p.p_dec);
             h = keep ? h * (1.f / (1.f - p.p_dec)) : 0.f;
           }
@@ -870,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       }
       __syncthreads();
       if (has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel && tid == 0) {   // the gate CTA
-        *p.n_steps = t + 1;
+        atomicMax(p.n_steps, t + 1);
         if (p.infer && *s_live == 0) ctrl->all_done = 1;
         __threadfence();
       }
@@ -917,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     const int ns = p.infer ? t : p.cap;
     for (int b = tid; b < p.B; b += kThreads)
       if (!p.infer || !__ldcg(&ctrl->done[b])) p.mel_lengths[b] = ns;
-    if (tid == 0) *p.n_steps = ns;
+    if (tid == 0) atomicMax(p.n_steps, ns);
   }
   if (p.cluster > 1) {
     // every stage this CTA filled has been released by all peers (their commits arrive on OUR
@@ -958,7 +946,6 @@ size_t persistent_ws_bytes(int B, int T, int cap) {
 bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
   if (!m->pk) return false;
   if (m->sm_count < kG) return false;
-  if (a->B > kRows) return false;
   if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
   return true;
 }
@@ -1059,16 +1046,28 @@ void persistent_pack_destroy(T2Model* m) {
   m->pk = nullptr;
 }
 
+static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t s, int b0, int nb);
+
 int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
+  // batch rows are independent: more than 64 rows run as consecutive launches of <= 64 rows
+  T2_CUDA(cudaMemsetAsync(a->n_steps, 0, sizeof(int32_t), s));
+  for (int b0 = 0; b0 < a->B; b0 += kRows) {
+    const int nb = a->B - b0 < kRows ? a->B - b0 : kRows;
+    T2_TRY(run_persistent_slice(m, a, s, b0, nb));
+  }
+  return T2_OK;
+}
+
+static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t s, int b0, int nb) {
   PersistentPack* pk = (PersistentPack*)m->pk;
-  const int B = a->B, T = a->T_enc, cap = a->n_steps_cap;
+  const int B = nb, T = a->T_enc, cap = a->n_steps_cap;
   DecoderWs w;
   T2_TRY(decoder_ws_carve(a, &w));
   T2_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(DecoderCtrl), s));
   T2_CUDA(cudaMemsetAsync(w.persistent, 0, (size_t)(4 + 16 + 8 + 16 + 4) * kXChunkBytes + (size_t)kRows * kAtt * 4, s));  // zero images (model.py:258-284)
   {  // processed_memory = memory_layer(memory)                                  (model.py:288)
     GemmArgs g;
-    g.seg[0] = {a->memory, kEnc, m->w[W_ATT_MEMORY], kEnc, kEnc};
+    g.seg[0] = {a->memory + (size_t)b0 * T * kEnc, kEnc, m->w[W_ATT_MEMORY], kEnc, kEnc};
     g.M = B * T; g.N = kAtt; g.C = w.pm; g.ldc = kAtt;
     T2_TRY(gemm_f32(g, s));
   }
@@ -1087,10 +1086,13 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
     const char* e = getenv("T2_L2_PIN_FRAC");   // fraction of weight-image lines kept with evict_last priority
     p.l2_pin_frac = e ? (float)atof(e) : 0.5f;
   }
-  p.memory = a->memory; p.pm = w.pm; p.mem_len = a->memory_lengths;
+  p.memory = a->memory + (size_t)b0 * T * kEnc; p.pm = w.pm;
+  p.mem_len = a->memory_lengths ? a->memory_lengths + b0 : nullptr;
   p.prenet_keep = a->prenet_keep; p.att_keep = a->att_keep; p.dec_keep = a->dec_keep;
-  p.mel = a->mel; p.gate = a->gate; p.align = a->align; p.mel_lengths = a->mel_lengths; p.n_steps = a->n_steps;
+  p.mel = a->mel + (size_t)b0 * cap * kMel; p.gate = a->gate + (size_t)b0 * cap; p.align = a->align + (size_t)b0 * cap * T;
+  p.mel_lengths = a->mel_lengths + b0; p.n_steps = a->n_steps;
   p.ctrl = w.ctrl;
+  p.b0 = b0; p.Btot = a->B;
   p.B = B; p.T = T; p.cap = cap; p.infer = a->mode == T2_MODE_INFER; p.training = a->training;
   p.gate_threshold = a->gate_threshold; p.score_mask_value = a->score_mask_value;
   p.p_att = m->cfg.p_attention_dropout; p.p_dec = m->cfg.p_decoder_dropout; p.seed = a->seed;
@@ -1099,7 +1101,7 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
     // them once into x2 operand images, the kernel then skips the prenet events and their two barriers
     uint8_t* timg = (uint8_t*)p.q + (size_t)kRows * kAtt * 4;
     timg = (uint8_t*)(((uintptr_t)timg + 1023) & ~(uintptr_t)1023);
-    rows_to_image_kernel<<<dim3(4, cap), 256, 0, s>>>(a->teacher_prenet, kPre, B, kPre, (long)B * kPre, timg,
+    rows_to_image_kernel<<<dim3(4, cap), 256, 0, s>>>(a->teacher_prenet + (size_t)b0 * kPre, kPre, B, kPre, (long)a->B * kPre, timg,
                                                       (long)4 * kXChunkBytes);
     T2_LAUNCH_CHECK();
     p.teacher_x2_img = timg;
@@ -1115,7 +1117,7 @@ int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s) {
   }
   {
     const char* e = getenv("T2_HIER_BARRIER");   // 0 = flat 128-way barrier
-    p.hier_barrier = e ? atoi(e) : 1;
+    p.hier_barrier = e ? atoi(e) : 0;   // measured slower than the flat barrier on B200 (profiles/r01)
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
