@@ -244,6 +244,31 @@ __device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& ta
   ptx::fence_proxy_async();
 }
 
+// split-phase form of the flat barrier: arrive as soon as this CTA's contribution is written, do work that
+// does not depend on the other CTAs, then wait
+__device__ __forceinline__ void grid_arrive(DecoderCtrl* ctrl, unsigned int& target) {
+  ptx::fence_proxy_async();
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(DecoderCtrl* ctrl, unsigned int target) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = clock64();
+    while (true) {
+      unsigned int c;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->bar_count) : "memory");
+      if ((int)(c - target) >= 0) break;
+      if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 101);
+    }
+  }
+  __syncthreads();
+  ptx::fence_proxy_async();
+}
+
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
@@ -599,87 +624,99 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       T2_PROF(3);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B2: q complete
-      T2_PROF(4);
     }
     // ======== attention for batch row (cta mod 64) ============================ model.py:43-86, 358-365
-    if ((cta & 63) < p.B) {
-      // CTAs b and b+64 both evaluate row b's energies / softmax (no exchange needed, bit-identical);
-      // each produces one half of the context columns, the first writes the alignment row
-      const int b = cta & 63, ahalf = cta >> 6;
-      for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
+    // CTAs b and b+64 both evaluate row b's energies / softmax (no exchange needed, bit-identical); each
+    // produces one half of the context columns, the first writes the alignment row.  Everything that only
+    // needs THIS CTA's state (im2col of its attention weights, the pa GEMM, staging encoder memory rows)
+    // runs between the arrival at barrier B2 and the wait for it.
+    const bool att_cta = (cta & 63) < p.B;
+    const int att_b = cta & 63, ahalf = cta >> 6;
+    uint8_t* aimg = rg.stage0;
+    const int smem_rows = min(T, (kStages * kStageBytes) / (kEnc / 2 * 4));   // memory rows staged in the ring
+    auto att_im2col_mma = [&](int t0, int nt) {
+      const int j_end = min(T, (t0 + nt) * 128);
+      // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
+      //     SWIZZLE_128B tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
+      //     accumulator rows are never read                                        model.py:23
+      for (int item = t0 * 128 * 8 + tid; item < j_end * 8; item += kThreads) {
+        const int j = item >> 3, g8 = item & 7;
+        const int tile = (j >> 7) - t0, r = j & 127;
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int kk = g8 * 8 + e;
+          float v = 0.f;
+          if (kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
+          split_fp16(v, hh[e], ll[e]);
+        }
+        uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) * 16);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
+      }
+      ptx::fence_proxy_async();
+      __syncthreads();
+      // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
+      //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
+      if (warp == 1) {
+        if (lane == 0) {
+          ptx::tc_fence_after();
+          const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
+          const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+          for (int tile = 0; tile < nt; ++tile) {
+            const uint32_t d = tmem_base + kColAtt + tile * 128;
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              const uint64_t a_hi = ptx::make_sw128_desc(as + tile * 32768 + kk * 32);
+              const uint64_t a_lo = ptx::make_sw128_desc(as + tile * 32768 + 16384 + kk * 32);
+              const uint64_t b_hi = ptx::make_sw128_desc(bs + kk * 32);
+              const uint64_t b_lo = ptx::make_sw128_desc(bs + 16384 + kk * 32);
+              ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
+              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(rg.acc);
+        }
+        __syncwarp();
+      }
+    };
+    auto stage_memory_rows = [&](int j0, int j1) {     // cp.async this CTA's half of memory rows [j0, j1) into the ring
+      const uint32_t sbase = ptx::smem_u32(rg.stage0);
+      const float* msrc = p.memory + (long)att_b * T * kEnc + ahalf * (kEnc / 2);
+      for (int i = j0 * 64 + tid; i < j1 * 64; i += kThreads) {
+        const int j = i >> 6, c4 = i & 63;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)i * 16u),
+                     "l"(msrc + (long)j * kEnc + c4 * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    grid_arrive(ctrl, bar_target);                                             // B2 (arrive): q written
+    if (att_cta) {
       for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
-      uint8_t* aimg = rg.stage0;
-      const int smem_rows = min(T, (kStages * kStageBytes) / (kEnc / 2 * 4));   // memory rows staged in the ring
+      att_im2col_mma(0, min(2, ntiles));
+      if (smem_rows > 64) stage_memory_rows(64, smem_rows);   // ring space beyond the 2-tile A image
+    }
+    T2_PROF(15);
+    grid_wait(ctrl, bar_target);                                               // B2 (wait): q complete
+    T2_PROF(4);
+    if (att_cta) {
+      const int b = att_b;
+      for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
+      __syncthreads();
       for (int t0 = 0; t0 < ntiles; t0 += 2) {            // rounds of up to 2 tiles of 128 positions
         const int nt = min(2, ntiles - t0);
-        const int j_end = min(T, (t0 + nt) * 128);
         int nact = 0;
         for (int tl = 0; tl < nt; ++tl)
           if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
-        // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
-        //     SWIZZLE_128B tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
-        //     accumulator rows are never read                                        model.py:23
-        for (int item = t0 * 128 * 8 + tid; item < j_end * 8; item += kThreads) {
-          const int j = item >> 3, g8 = item & 7;
-          const int tile = (j >> 7) - t0, r = j & 127;
-          __align__(16) __half hh[8];
-          __align__(16) __half ll[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int kk = g8 * 8 + e;
-            float v = 0.f;
-            if (kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
-            split_fp16(v, hh[e], ll[e]);
-          }
-          uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) * 16);
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
-          *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
-        }
-        ptx::fence_proxy_async();
-        __syncthreads();
-        T2_PROF(15);
-        // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
-        //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
-        if (warp == 1) {
-          if (lane == 0) {
-            ptx::tc_fence_after();
-            const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
-            const uint32_t idesc = ptx::make_idesc_f16(128, 128);
-            for (int tile = 0; tile < nt; ++tile) {
-              const uint32_t d = tmem_base + kColAtt + tile * 128;
-#pragma unroll
-              for (int kk = 0; kk < kChunkK / 16; ++kk) {
-                const uint64_t a_hi = ptx::make_sw128_desc(as + tile * 32768 + kk * 32);
-                const uint64_t a_lo = ptx::make_sw128_desc(as + tile * 32768 + 16384 + kk * 32);
-                const uint64_t b_hi = ptx::make_sw128_desc(bs + kk * 32);
-                const uint64_t b_lo = ptx::make_sw128_desc(bs + 16384 + kk * 32);
-                ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
-                ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
-                ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
-              }
-            }
-            ptx::umma_commit(rg.acc);
-          }
-          __syncwarp();
-        }
+        if (t0 > 0) att_im2col_mma(t0, nt);
         mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
         rg.acc_phase ^= 1;
         ptx::tc_fence_after();
         T2_PROF(16);
-        if (t0 + 2 >= ntiles) {
-          // the ring is idle until the next event: stage this CTA's half of the encoder memory rows in it
-          // with cp.async while the energies / softmax run (consumed by the context product below)
-          const uint32_t sbase = ptx::smem_u32(rg.stage0);
-          const float* msrc = p.memory + (long)b * T * kEnc + ahalf * (kEnc / 2);
-          for (int i = tid; i < smem_rows * (kEnc / 2 / 4); i += kThreads) {
-            const int j = i >> 6, c4 = i & 63;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)i * 16u),
-                         "l"(msrc + (long)j * kEnc + c4 * 4)
-                         : "memory");
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
+        if (t0 + 2 >= ntiles) stage_memory_rows(0, min(64, smem_rows));   // the A image region is free now
         // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
         //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
         {
@@ -1116,8 +1153,10 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
     if (want != 1 && want != 2 && want != 4 && want != 8) want = 8;
   }
   {
-    const char* e = getenv("T2_HIER_BARRIER");   // 0 = flat 128-way barrier
-    p.hier_barrier = e ? atoi(e) : 0;   // measured slower than the flat barrier on B200 (profiles/r01)
+    // the hierarchical (cluster barrier + 1 poller per cluster) variant measured slower than the flat
+    // 128-way barrier on B200 (profiles/r01_decoder_v10_ncu_summary.md) and is not combined with the
+    // split-phase B2 barrier: kept in the source for reference, always off
+    p.hier_barrier = 0;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
