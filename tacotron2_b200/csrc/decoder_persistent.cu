@@ -56,9 +56,9 @@ constexpr int kColAtt = 160;                              // attention pa accumu
 constexpr int kTmemCols = 512;
 constexpr int kWStageMax = 2 * kHiCols * kChunkK * 2;    // hi + lo planes of up to 80 weight rows = 20 KiB
 constexpr int kStageBytes = kXChunkBytes + kWStageMax;   // 36 KiB
-constexpr int kNumEvents = 5;         // x2, ah, ctx, dh, x1
-constexpr int kPCols = 344;           // 80 mel + 1 gate + 256 x1 + 7 pad
-constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 43;
+constexpr int kNumEvents = 6;         // x2, ah, ctx, dh (projection), x1, dh (next decoder gates)
+constexpr int kPCols = 384;           // 80 mel + 1 gate + 256 x1 + 47 pad (48 CTAs x 8: cluster aligned)
+constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 48;
 constexpr int kWeffBytes = kAtt * kChunkK * 2 * 2;        // fused location filter image (hi+lo) = 32 KiB
 constexpr int kXchStride = 33;
 constexpr unsigned long long kWatchdogCycles = 1ull << 32;   // ~2 s
@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_xch = reinterpret_cast<float*>(sp); sp += kRows * kXchStride * 4;  // lo-row halves of the accumulators
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(sp); sp += kRows * 4;        // prenet keep bits of step t+1 (8 per row)
+  float* s_bias_p = reinterpret_cast<float*>(sp); sp += 8 * 4;                // bias of this CTA's 8 projection columns
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
   float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128]
@@ -490,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     rg.pol_x = ptx::policy_evict_last();
   }
   for (int i = tid; i < kAtt; i += kThreads) s_v[i] = p.w_v[i];
+  if (tid < 8) s_bias_p[tid] = (cta >= kPCta0 && cta < kPCta0 + kPCtas) ? p.bias_p[(cta - kPCta0) * 8 + tid] : 0.f;
   for (int i = tid; i < TP; i += kThreads) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }   // model.py:274-277
   ptx::fence_proxy_async();       // s_weff is read by tcgen05.mma (async proxy)
   ptx::tc_fence_before();
@@ -577,8 +579,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
       }
-      // the otherwise idle lo-row lanes of column group 0 draw the prenet dropout bits this CTA will need
-      // at the END of this step (x1 columns on the projection CTAs, x2 columns on the prenet-2 CTAs)
+      T2_PROF(1);
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B1: ah_t complete
+      T2_PROF(2);
+    }
+    // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
+    {
+      // while the producer / MMA threads stream this event, the otherwise idle lo-row lanes of column group 0
+      // (warps 2, 3) draw the prenet dropout bits this CTA needs at the END of this step (x1 columns on the projection CTAs, x2 columns on the prenet-2 CTAs)
       if (p.infer && is_lo && cg == 0 && row < p.B && t + 1 < p.cap && (has_p || has_x2)) {
         uint32_t bits = 0;
         if (has_x2) {
@@ -602,12 +610,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         s_mask[row] = bits;
       }
-      T2_PROF(1);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B1: ah_t complete
-      T2_PROF(2);
-    }
-    // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
-    {
       run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr);   // the attention phase reuses the ring as scratch
       if (has_q) {
         float g[8];
@@ -847,70 +849,98 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B4: dh_t complete
       T2_PROF(9);
     }
-    // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
+    // ======== E3a: dh_t -> projection (rest) on the 48 projection CTAs; epilogue -> mel, gate, stop latch, x1
     {
-      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl,
-                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr);   // INFER: the loop may end after this step
+      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl, &plan.ev[5]);
       T2_PROF(10);
-      if (tid == 0) *s_live = 0;
-      float g[8];
-      if (has_p && cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
-      if (has_p && cg == 0 && is_lo) {
+      if (has_p) {
+        if (tid == 0) *s_live = 0;
+        float g[8];
+        if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
+        if (cg == 0 && is_lo) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
-      }
-      ptx::tc_fence_before();
-      __syncthreads();
-      if (has_p && cg == 0 && erow) {
-        const int pc0 = (cta - kPCta0) * 8;
+          for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (cg == 0 && erow) {
+          const int pc0 = (cta - kPCta0) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int pc = pc0 + j;
-          const float v = g[j] + s_xch[row * kXchStride + j] + p.bias_p[pc];
-          if (pc < kMel) {
-            p.mel[((long)row * p.cap + t) * kMel + pc] = v;                    // model.py:375-376
-          } else if (pc == kMel) {
-            p.gate[(long)row * p.cap + t] = v;                                 // model.py:378
-            if (p.infer) {
-              int done = ctrl->done[row];
-              if (!done && sigmoid_exact(v) > p.gate_threshold) {             // model.py:443
-                done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
+          for (int j = 0; j < 8; ++j) {
+            const int pc = pc0 + j;
+            const float v = g[j] + s_xch[row * kXchStride + j] + s_bias_p[j];
+            if (pc < kMel) {
+              p.mel[((long)row * p.cap + t) * kMel + pc] = v;                    // model.py:375-376
+            } else if (pc == kMel) {
+              p.gate[(long)row * p.cap + t] = v;                                 // model.py:378
+              if (p.infer) {
+                int done = ctrl->done[row];
+                if (!done && sigmoid_exact(v) > p.gate_threshold) {             // model.py:443
+                  done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
+                }
+                if (!done) atomicAdd(s_live, 1);
               }
-              if (!done) atomicAdd(s_live, 1);
-            }
-          } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
-            const int col = pc - (kMel + 1);
-            float r = fmaxf(v, 0.f);
-            if (p.infer && t + 1 < p.cap) r = ((s_mask[row] >> j) & 1u) ? r * 2.f : 0.f;
-            if (p.infer) {
-              __half h, l;
-              split_fp16(r, h, l);
-              __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
-              __half* lo = hi + kRows * kChunkK;
-              const uint32_t e = img_elem_offset(row, col & 63);
-              hi[e] = h; lo[e] = l;
+            } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
+              const int col = pc - (kMel + 1);
+              float r = fmaxf(v, 0.f);
+              if (p.infer && t + 1 < p.cap) r = ((s_mask[row] >> j) & 1u) ? r * 2.f : 0.f;
+              if (p.infer) {
+                __half h, l;
+                split_fp16(r, h, l);
+                __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
+                __half* lo = hi + kRows * kChunkK;
+                const uint32_t e = img_elem_offset(row, col & 63);
+                hi[e] = h; lo[e] = l;
+              }
             }
           }
         }
-      }
-      __syncthreads();
-      if (has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel && tid == 0) {   // the gate CTA
-        atomicMax(p.n_steps, t + 1);
-        if (p.infer && *s_live == 0) ctrl->all_done = 1;
-        __threadfence();
+        // publish x1 (and the stop flag) to the prenet-2 CTAs: a 48-way arrival counter, not a grid barrier
+        ptx::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          if ((cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel) {     // the CTA that owns the gate column
+            atomicMax(p.n_steps, t + 1);
+            if (p.infer && *s_live == 0) ctrl->all_done = 1;
+          }
+          if (p.infer) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->x1_count) : "memory");
+          }
+        }
       }
       T2_PROF(11);
-      if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B5: x1 / stop flag complete
-      T2_PROF(12);
-      int all_done;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
-      if (all_done || t + 1 == p.cap) { ++t; break; }
     }
-    // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
+    // ======== E3b: dh_t -> next step's decoder gates (recurrent part), every CTA ================ model.py:368
     {
-      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0]);   // step t+1 is certain here
+      run_event(rg, plan.ev[5], p.dh_img, p.wimg, 16, tmem_base, ctrl,
+                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr);   // INFER: the loop may end after this step
+      T2_PROF(20);
+      if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
+    }
+    // ======== E4: x1 -> x2_(t+1) (second prenet layer) on the 32 prenet-2 CTAs ============== model.py:97-100
+    {
+      bool run_e4 = false;
       if (has_x2) {
+        if (tid == 0) {
+          const unsigned int want = (unsigned int)kPCtas * (unsigned int)(t + 1);
+          const unsigned long long t0 = clock64();
+          while (true) {
+            unsigned int c;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->x1_count) : "memory");
+            if ((int)(c - want) >= 0) break;
+            if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 102);
+          }
+        }
+        __syncthreads();
+        ptx::fence_proxy_async();
+        int ad;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ad) : "l"(&ctrl->all_done) : "memory");
+        run_e4 = !ad && t + 1 < p.cap;
+      }
+      T2_PROF(12);
+      if (run_e4) {
+        run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0]);   // step t+1 is certain here
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
         if (cg == 0 && is_lo) {
@@ -922,7 +952,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (cg == 0 && erow) {
           const int col0 = (cta - kX2Cta0) * 8;
           float r[8];
-#pragma unroll
           const uint32_t bits = s_mask[row];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -932,8 +961,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       T2_PROF(13);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B6: x2_(t+1) complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                         // B6: x2_(t+1) / stop flag complete
       T2_PROF(14);
+      int all_done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
+      if (all_done || t + 1 == p.cap) { ++t; break; }
     }
   }
   // rows that never fired: length = number of steps run (model.py:445-447)
@@ -969,7 +1001,7 @@ static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
   return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
-         (size_t)kRows * kXchStride * 4 + kRows * 4 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
+         (size_t)kRows * kXchStride * 4 + kRows * 4 + 32 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
 }
 
 size_t persistent_ws_bytes(int B, int T, int cap) {
@@ -1010,8 +1042,9 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
     set(0, 4, kColA, {32});
     if (hq) set(1, 16, kColA, {32, 32, 16}); else set(1, 16, kColA, {32, 32});
     if (hp) set(2, 8, kColA, {32, 32, 16}); else set(2, 8, kColA, {32, 32});
-    if (hp) set(3, 16, kColD, {32, 16}); else set(3, 16, kColD, {32});
+    if (hp) set(3, 16, kColS, {16}); else { pl.ev[3].w_off = (uint32_t)off; }     // projection CTAs only
     if (hx) set(4, 4, kColS, {16}); else { pl.ev[4].w_off = (uint32_t)off; }
+    set(5, 16, kColD, {32});                                                      // next step's decoder gates
   }
   if (off >= (size_t)4 << 30) return fail(T2_ERR_INVALID, "W image too large");
   if (!pk->wimg) {
@@ -1068,8 +1101,8 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
   T2_TRY(pack(m->w[W_ARNN_WIH], kPre + kEnc, kPre, 8, r_lstm, 2, 0));         // E2: att' <- ctx
   T2_TRY(pack(m->w[W_DRNN_WIH], kdc, kARnn, 8, r_lstm, 2, 1));                //     dec <- ctx
   T2_TRY(pack(pk->wp_all, kdc, kDRnn, 8, r_p, 2, 2));                         //     P <- ctx
-  T2_TRY(pack(m->w[W_DRNN_WHH], kDRnn, 0, 16, r_lstm, 3, 0));                 // E3: dec' <- dh
-  T2_TRY(pack(pk->wp_all, kdc, 0, 16, r_p, 3, 1));                            //     P <- dh
+  T2_TRY(pack(pk->wp_all, kdc, 0, 16, r_p, 3, 0));                            // E3a: P <- dh
+  T2_TRY(pack(m->w[W_DRNN_WHH], kDRnn, 0, 16, r_lstm, 5, 0));                 // E3b: dec' <- dh
   T2_TRY(pack(m->w[W_PRENET1], kPre, 0, 4, r_x2, 4, 0));                      // E4: x2 <- x1
   return T2_OK;
 }
