@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt2b200.so")
+LIB_PATH = os.environ.get("T2B200_LIB") or os.path.join(_HERE, "libt2b200.so")   # T2B200_LIB: A/B test builds
 
 T2_NUM_WEIGHTS = 84
 IMPL_AUTO, IMPL_STEPWISE, IMPL_PERSISTENT = 0, 1, 2

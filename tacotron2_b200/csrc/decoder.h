@@ -12,8 +12,7 @@ struct DecoderCtrl {
   int pad_[2];
   unsigned int bar_count;  // grid barrier of the persistent kernel
   unsigned int bar_gen;
-  unsigned int x1_count;   // projection CTAs that have published x1 / the stop flag (monotonic)
-  int pad2_[1];
+  int pad2_[2];
   int done[kMaxBatch];     // per-row stop latch
   long long prof[3][24];   // cycles per phase of the persistent kernel, sampled on CTAs 0 / 60 / 100
 };

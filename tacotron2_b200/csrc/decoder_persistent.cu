@@ -57,8 +57,8 @@ constexpr int kTmemCols = 512;
 constexpr int kWStageMax = 2 * kHiCols * kChunkK * 2;    // hi + lo planes of up to 80 weight rows = 20 KiB
 constexpr int kStageBytes = kXChunkBytes + kWStageMax;   // 36 KiB
 constexpr int kNumEvents = 5;         // x2, ah, ctx, dh, x1
-constexpr int kPCols = 384;           // 80 mel + 1 gate + 256 x1 + 47 pad (48 CTAs x 8: cluster aligned)
-constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 48;
+constexpr int kPCols = 344;           // 80 mel + 1 gate + 256 x1 + 7 pad
+constexpr int kQCta0 = 0, kQCtas = 16, kX2Cta0 = 16, kX2Ctas = 32, kPCta0 = 48, kPCtas = 43;
 constexpr int kWeffBytes = kAtt * kChunkK * 2 * 2;        // fused location filter image (hi+lo) = 32 KiB
 constexpr int kXchStride = 33;
 constexpr unsigned long long kWatchdogCycles = 1ull << 32;   // ~2 s
@@ -283,114 +283,78 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
-// Ring geometry of an event: the operand ring (kRingBytes of shared memory) is cut into as many stages as
-// fit for THAT event's stage size (activation chunk + the largest weight chunk any CTA has for it): the
-// ring is latency bound (bytes in flight / bulk-copy latency), so events with small weight chunks get
-// more stages in flight.  Geometry is the same on every CTA (multicast writes land at equal offsets).
-struct Geom { uint32_t bytes, n; };
-constexpr int kMaxStages = 8;
-constexpr int kRingBytes = kStages * kStageBytes;   // 144 KiB
-
 struct Ring {
-  uint8_t* stage0;
-  __device__ __forceinline__ uint8_t* stage(uint32_t s) const { return stage0 + s * g.bytes; }
-  Geom g;             // geometry of the current event
-  uint64_t* full;     // [kMaxStages]
-  uint64_t* empty;    // [kMaxStages]
+  uint8_t* stage0;    // kStages buffers of kStageBytes each
+  __device__ __forceinline__ uint8_t* stage(uint32_t s) const { return stage0 + s * kStageBytes; }
+  uint64_t* full;     // [kStages]
+  uint64_t* empty;    // [kStages]
   uint64_t* acc;      // accumulator-ready barrier
-  uint32_t p_stage;            // producer cursor (thread 0 of warp 0)
-  uint32_t e_used, e_par;      // producer: stages filled at least once / parity of the release to wait for
-  uint32_t c_stage, f_par;     // consumer cursor and per-stage parity of the full barriers (thread 0 of warp 1)
+  uint32_t p_stage, p_phase;   // producer cursor (thread 0 of warp 0)
+  uint32_t c_stage, c_phase;   // consumer cursor (thread 0 of warp 1)
   uint32_t acc_phase;          // all threads
   uint64_t pol_x, pol_w;       // L2 eviction policies of the activation / weight streams
   uint32_t cs, rank;           // cluster size (1 = no multicast) and this CTA's rank in it
   uint32_t pre;                // stages whose weight chunk was already issued for the upcoming event
 };
 
-// producer: make stage s reusable (its previous fill has been released by every consumer), then note the fill
-__device__ __forceinline__ void ring_acquire(Ring& rg, uint32_t s, DecoderCtrl* ctrl) {
-  const uint32_t bit = 1u << s;
-  if (rg.e_used & bit) {
-    mbar_wait(&rg.empty[s], (rg.e_par >> s) & 1u, ctrl, 200);
-    rg.e_par ^= bit;
-  } else {
-    rg.e_used |= bit;
-  }
-}
-// producer: every fill issued so far has been released (needed before the stage boundaries move)
-__device__ __forceinline__ void ring_drain(Ring& rg, DecoderCtrl* ctrl) {
-  for (uint32_t s = 0; s < kMaxStages; ++s)
-    if ((rg.e_used >> s) & 1u) mbar_wait(&rg.empty[s], (rg.e_par >> s) & 1u, ctrl, 204);
-}
-
 // Weight chunks do not depend on the grid barrier that separates two events (only the activation does):
-// once the current event's stages are released the producer switches to the NEXT event's geometry, arms
-// its first stages and issues their weight copies, so their L2 / HBM latency overlaps the epilogue and the
-// barrier.
-__device__ __forceinline__ void prefetch_weights(Ring& rg, const EventPlan& nx, Geom ng, int chunks_next,
-                                                 const uint8_t* w_img, DecoderCtrl* ctrl) {
-  ring_drain(rg, ctrl);
-  rg.g = ng;
-  const int n = (int)ng.n < chunks_next ? (int)ng.n : chunks_next;
-  for (int i = 0; i < n; ++i) {
-    ring_acquire(rg, (uint32_t)i, ctrl);
-    ptx::mbar_arrive_expect_tx(&rg.full[i], kXChunkBytes + nx.w_bytes);
-    ptx::bulk_g2s_hint(rg.stage(i) + kXChunkBytes, w_img + nx.w_off + (size_t)i * nx.w_bytes, nx.w_bytes,
-                       &rg.full[i], rg.pol_w);
+// the producer arms the first kStages stages of the NEXT event and issues their weight copies right after
+// the current event's last chunk, so their L2 / HBM latency overlaps the epilogue and the barrier.
+__device__ __forceinline__ void prefetch_weights(Ring& rg, const EventPlan& nx, const uint8_t* w_img,
+                                                 DecoderCtrl* ctrl) {
+  uint32_t s = rg.p_stage, ph = rg.p_phase;
+  for (int i = 0; i < kStages; ++i) {
+    mbar_wait(&rg.empty[s], ph ^ 1, ctrl, 205);
+    ptx::mbar_arrive_expect_tx(&rg.full[s], kXChunkBytes + nx.w_bytes);
+    ptx::bulk_g2s_hint(rg.stage(s) + kXChunkBytes, w_img + nx.w_off + (size_t)i * nx.w_bytes, nx.w_bytes,
+                       &rg.full[s], rg.pol_w);
+    if (++s == kStages) { s = 0; ph ^= 1; }
   }
-  rg.pre = (uint32_t)n;
+  rg.pre = kStages;
 }
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight rows through the ring
 // and issues the MMAs (1 per 16-wide K step).  Called by all threads; returns after the accumulators are
 // complete.  Every MMA accumulates (the epilogues zero what they consume).
-__device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, Geom geom, const uint8_t* x_img,
+__device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
                                           const uint8_t* w_img, int chunks, uint32_t tmem_base,
-                                          DecoderCtrl* ctrl, const EventPlan* next, Geom next_geom, int next_chunks) {
+                                          DecoderCtrl* ctrl, const EventPlan* next) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (ep.nrows == 0) {                 // this CTA (and its whole cluster) has no consumer of this activation
-    if (threadIdx.x == 0 && next != nullptr && next->nrows != 0 && rg.pre == 0)
-      prefetch_weights(rg, *next, next_geom, next_chunks, w_img, ctrl);
+    if (threadIdx.x == 0 && next != nullptr && next->nrows != 0 && rg.pre == 0) prefetch_weights(rg, *next, w_img, ctrl);
     return;
   }
   if (warp == 0) {
     if (lane == 0) {
-      if (rg.pre == 0) { ring_drain(rg, ctrl); rg.g = geom; }   // (a prefetch already switched the geometry)
-      rg.p_stage = 0;
       for (int i = 0; i < chunks; ++i) {
-        const uint32_t sidx = rg.p_stage;
-        uint8_t* st = rg.stage(sidx);
+        uint8_t* st = rg.stage(rg.p_stage);
         if ((uint32_t)i >= rg.pre) {     // not armed / issued ahead of time
-          ring_acquire(rg, sidx, ctrl);
-          ptx::mbar_arrive_expect_tx(&rg.full[sidx], kXChunkBytes + ep.w_bytes);
+          mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 200);
+          ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
           ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
-                             &rg.full[sidx], rg.pol_w);
+                             &rg.full[rg.p_stage], rg.pol_w);
         }
         if (rg.cs == 1) {
-          ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[sidx], rg.pol_x);
+          ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
         } else {   // every CTA of the cluster fetches 1/cs of the activation chunk and multicasts it to all
           const uint32_t slice = kXChunkBytes / rg.cs;
           ptx::bulk_g2s_mc_hint(st + rg.rank * slice, x_img + (size_t)i * kXChunkBytes + rg.rank * slice, slice,
-                                &rg.full[sidx], (uint16_t)((1u << rg.cs) - 1u), rg.pol_x);
+                                &rg.full[rg.p_stage], (uint16_t)((1u << rg.cs) - 1u), rg.pol_x);
         }
-        if (++rg.p_stage == rg.g.n) rg.p_stage = 0;
+        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
       }
       rg.pre = 0;
-      if (next != nullptr && next->nrows != 0) prefetch_weights(rg, *next, next_geom, next_chunks, w_img, ctrl);
+      if (next != nullptr && next->nrows != 0) prefetch_weights(rg, *next, w_img, ctrl);
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      rg.g = geom;
-      rg.c_stage = 0;
       const uint32_t idesc = ptx::make_idesc_f16(128, 2u * (uint32_t)ep.nrows);
       const uint32_t d = tmem_base + (uint32_t)ep.col0;
       for (int i = 0; i < chunks; ++i) {
-        const uint32_t sidx = rg.c_stage;
-        mbar_wait(&rg.full[sidx], (rg.f_par >> sidx) & 1u, ctrl, 201);
-        rg.f_par ^= 1u << sidx;
+        mbar_wait(&rg.full[rg.c_stage], rg.c_phase, ctrl, 201);
         ptx::tc_fence_after();
-        const uint32_t xs = ptx::smem_u32(rg.stage(sidx));
+        const uint32_t xs = ptx::smem_u32(rg.stage(rg.c_stage));
         const uint32_t ws = xs + kXChunkBytes;
 #pragma unroll
         for (int kk = 0; kk < kChunkK / 16; ++kk) {
@@ -398,9 +362,9 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, Geom ge
           const uint64_t b = ptx::make_sw128_desc(ws + kk * 32);                          // [W_hi ; W_lo] per consumer
           ptx::umma_f16(d, a, b, idesc, 1u);
         }
-        if (rg.cs == 1) ptx::umma_commit(&rg.empty[sidx]);   // frees the stage once these MMAs have read it
-        else ptx::umma_commit_mc(&rg.empty[sidx], (uint16_t)((1u << rg.cs) - 1u));
-        if (++rg.c_stage == rg.g.n) rg.c_stage = 0;
+        if (rg.cs == 1) ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
+        else ptx::umma_commit_mc(&rg.empty[rg.c_stage], (uint16_t)((1u << rg.cs) - 1u));
+        if (++rg.c_stage == kStages) { rg.c_stage = 0; rg.c_phase ^= 1; }
       }
       ptx::umma_commit(rg.acc);
     }
@@ -491,8 +455,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   Ring rg;
   rg.stage0 = sp; sp += kStages * kStageBytes;
   uint8_t* s_weff = sp; sp += kWeffBytes;                                     // fused location filter image
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 24 * sizeof(uint64_t);
-  rg.full = bars; rg.empty = bars + kMaxStages; rg.acc = bars + 2 * kMaxStages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
+  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
   int* s_live = reinterpret_cast<int*>(sp); sp += 16;
   float* s_bias_a = reinterpret_cast<float*>(sp); sp += 32 * 4;
@@ -507,13 +471,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
   float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128]
 
-  rg.p_stage = rg.c_stage = rg.acc_phase = rg.e_used = rg.e_par = rg.f_par = 0;
-  rg.g.bytes = kStageBytes; rg.g.n = kStages;
+  rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
   rg.pre = 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
     ptx::mbar_init(rg.acc, 1);
     ptx::fence_barrier_init();
   }
@@ -539,8 +502,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 
   const CtaPlan& plan = p.plans[cta];
   DecoderCtrl* ctrl = p.ctrl;
-  // stage geometry per event: activation chunk (16 KiB) + the largest weight chunk of the event
-  const Geom gE0 = {24576u, 6u}, gE1 = {36864u, 4u}, gE2 = {36864u, 4u}, gE3 = {28672u, 5u}, gE4 = {20480u, 7u};
   unsigned int bar_target = 0;
   const uint32_t bar_cs = p.hier_barrier ? rg.cs : 1;
   // epilogue role of this thread: TMEM lane quadrant quad = warp % 4 (hardware rule), column group
@@ -592,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     // ======== E0: x2_t -> attention LSTM gates, epilogue -> ah_t ==================== model.py:352-356
     {
       const uint8_t* x2 = p.infer ? p.x2_img : p.teacher_x2_img + (size_t)t * 4 * kXChunkBytes;
-      run_event(rg, plan.ev[0], gE0, x2, p.wimg, 4, tmem_base, ctrl, &plan.ev[1], gE1, 16);
+      run_event(rg, plan.ev[0], x2, p.wimg, 4, tmem_base, ctrl, &plan.ev[1]);
       T2_PROF(0);
       float g[8];
       T2_TAKE_GATES(kColA, kNA, g);
@@ -649,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         s_mask[row] = bits;
       }
-      run_event(rg, plan.ev[1], gE1, p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr, gE2, 8);   // the attention phase reuses the ring as scratch
+      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr);   // the attention phase reuses the ring as scratch
       if (has_q) {
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
@@ -858,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     T2_PROF(6);
     // ======== E2: ctx_t -> dec gates (rest), next att gates, projection (part); epilogue -> dh_t
     {
-      run_event(rg, plan.ev[2], gE2, p.ctx_img, p.wimg, 8, tmem_base, ctrl, &plan.ev[3], gE3, 16);
+      run_event(rg, plan.ev[2], p.ctx_img, p.wimg, 8, tmem_base, ctrl, &plan.ev[3]);
       T2_PROF(7);
       float g[8];
       T2_TAKE_GATES(kColD, kND, g);
@@ -888,94 +849,70 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B4: dh_t complete
       T2_PROF(9);
     }
-    // ======== E3: dh_t -> next step's decoder gates (recurrent part, model.py:368) and, on the 48 projection
-    //          CTAs, the rest of the projection; epilogue -> mel, gate, stop latch, x1
+    // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
     {
-      run_event(rg, plan.ev[3], gE3, p.dh_img, p.wimg, 16, tmem_base, ctrl,
-                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr, gE0, 4);   // INFER: the loop may end after this step
+      run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl,
+                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr);   // INFER: the loop may end after this step
       T2_PROF(10);
-      if (has_p) {
-        if (tid == 0) *s_live = 0;
-        float g[8];
-        if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
-        if (cg == 0 && is_lo) {
+      if (tid == 0) *s_live = 0;
+      float g[8];
+      if (has_p && cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
+      if (has_p && cg == 0 && is_lo) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
-        }
-        ptx::tc_fence_before();
-        __syncthreads();
-        if (cg == 0 && erow) {
-          const int pc0 = (cta - kPCta0) * 8;
+        for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+      }
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (has_p && cg == 0 && erow) {
+        const int pc0 = (cta - kPCta0) * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int pc = pc0 + j;
-            const float v = g[j] + s_xch[row * kXchStride + j] + s_bias_p[j];
-            if (pc < kMel) {
-              p.mel[((long)row * p.cap + t) * kMel + pc] = v;                    // model.py:375-376
-            } else if (pc == kMel) {
-              p.gate[(long)row * p.cap + t] = v;                                 // model.py:378
-              if (p.infer) {
-                int done = ctrl->done[row];
-                if (!done && sigmoid_exact(v) > p.gate_threshold) {             // model.py:443
-                  done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
-                }
-                if (!done) atomicAdd(s_live, 1);
+        for (int j = 0; j < 8; ++j) {
+          const int pc = pc0 + j;
+          const float v = g[j] + s_xch[row * kXchStride + j] + s_bias_p[j];
+          if (pc < kMel) {
+            p.mel[((long)row * p.cap + t) * kMel + pc] = v;                    // model.py:375-376
+          } else if (pc == kMel) {
+            p.gate[(long)row * p.cap + t] = v;                                 // model.py:378
+            if (p.infer) {
+              int done = ctrl->done[row];
+              if (!done && sigmoid_exact(v) > p.gate_threshold) {             // model.py:443
+                done = 1; ctrl->done[row] = 1; p.mel_lengths[row] = t + 1;
               }
-            } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
-              const int col = pc - (kMel + 1);
-              float r = fmaxf(v, 0.f);
-              if (p.infer && t + 1 < p.cap) r = ((s_mask[row] >> j) & 1u) ? r * 2.f : 0.f;
-              if (p.infer) {
-                __half h, l;
-                split_fp16(r, h, l);
-                __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
-                __half* lo = hi + kRows * kChunkK;
-                const uint32_t e = img_elem_offset(row, col & 63);
-                hi[e] = h; lo[e] = l;
-              }
+              if (!done) atomicAdd(s_live, 1);
+            }
+          } else if (pc < kMel + 1 + kPre) {                                   // first prenet layer of step t+1
+            const int col = pc - (kMel + 1);
+            float r = fmaxf(v, 0.f);
+            if (p.infer && t + 1 < p.cap) r = ((s_mask[row] >> j) & 1u) ? r * 2.f : 0.f;
+            if (p.infer) {
+              __half h, l;
+              split_fp16(r, h, l);
+              __half* hi = reinterpret_cast<__half*>(p.x1_img + (size_t)(col >> 6) * kXChunkBytes);
+              __half* lo = hi + kRows * kChunkK;
+              const uint32_t e = img_elem_offset(row, col & 63);
+              hi[e] = h; lo[e] = l;
             }
           }
         }
-        // publish x1 (and the stop flag) to the prenet-2 CTAs: a 48-way arrival counter, not a grid barrier
-        ptx::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          if ((cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel) {     // the CTA that owns the gate column
-            atomicMax(p.n_steps, t + 1);
-            if (p.infer && *s_live == 0) ctrl->all_done = 1;
-          }
-          if (p.infer) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->x1_count) : "memory");
-          }
-        }
+      }
+      __syncthreads();
+      if (has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel && tid == 0) {   // the gate CTA
+        atomicMax(p.n_steps, t + 1);
+        if (p.infer && *s_live == 0) ctrl->all_done = 1;
+        __threadfence();
       }
       T2_PROF(11);
-    }
-    if (!p.infer) continue;                                                    // teacher forcing: x2 is precomputed
-    // ======== E4: x1 -> x2_(t+1) (second prenet layer) on the 32 prenet-2 CTAs ============== model.py:97-100
-    {
-      bool run_e4 = false;
-      if (has_x2) {
-        if (tid == 0) {
-          const unsigned int want = (unsigned int)kPCtas * (unsigned int)(t + 1);
-          const unsigned long long t0 = clock64();
-          while (true) {
-            unsigned int c;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->x1_count) : "memory");
-            if ((int)(c - want) >= 0) break;
-            if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 102);
-          }
-        }
-        __syncthreads();
-        ptx::fence_proxy_async();
-        int ad;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ad) : "l"(&ctrl->all_done) : "memory");
-        run_e4 = !ad && t + 1 < p.cap;
-      }
+      if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B5: x1 / stop flag complete
       T2_PROF(12);
-      if (run_e4) {
-        run_event(rg, plan.ev[4], gE4, p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0], gE0, 4);   // step t+1 is certain here
+      int all_done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
+      if (all_done || t + 1 == p.cap) { ++t; break; }
+    }
+    // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
+    {
+      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0]);   // step t+1 is certain here
+      if (has_x2) {
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
         if (cg == 0 && is_lo) {
@@ -996,11 +933,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       T2_PROF(13);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                         // B6: x2_(t+1) / stop flag complete
+      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B6: x2_(t+1) complete
       T2_PROF(14);
-      int all_done;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
-      if (all_done || t + 1 == p.cap) { ++t; break; }
     }
   }
   // rows that never fired: length = number of steps run (model.py:445-447)
@@ -1014,7 +948,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   if (p.cluster > 1) {
     // every stage this CTA filled has been released by all peers (their commits arrive on OUR
     // barriers) before anyone leaves, then leave together
-    if (tid == 0) ring_drain(rg, ctrl);
+    if (tid == 0)
+      for (int s = 0; s < kStages; ++s) {
+        mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 204);
+        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
+      }
     __syncthreads();
     ptx::cluster_sync_all();
   }
@@ -1031,7 +969,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
-  return (size_t)kStages * kStageBytes + kWeffBytes + 24 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
+  return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
          (size_t)kRows * kXchStride * 4 + kRows * 4 + 32 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
 }
 
@@ -1270,18 +1208,15 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   uint8_t* sp = smem_raw;
   Ring rg;
   rg.stage0 = sp; sp += kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 24 * sizeof(uint64_t);
-  rg.full = bars; rg.empty = bars + kMaxStages; rg.acc = bars + 2 * kMaxStages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
+  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
   float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
-  rg.p_stage = rg.c_stage = rg.acc_phase = rg.e_used = rg.e_par = rg.f_par = 0;
-  rg.g.bytes = kStageBytes; rg.g.n = kStages;
+  rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = rg.pol_w = ptx::policy_evict_last();
   rg.cs = 1; rg.rank = 0; rg.pre = 0;
-  // first pass with the 4 x 36 KiB geometry, second (prefetched) pass with 7 x 20 KiB when the weights fit
-  const Geom g1 = {36864u, 4u}, g2 = (ep.w_bytes <= 4096u) ? Geom{20480u, 7u} : Geom{36864u, 4u};
   if (tid == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);
     ptx::fence_barrier_init();
   }
@@ -1296,10 +1231,10 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   ptx::tmem_wait_st();
   ptx::tc_fence_before();
   __syncthreads();
-  run_event(rg, ep, g1, x_img, w_img, chunks, tmem_base, ctrl, &ep, g2, chunks);   // second pass: prefetched weights
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl, &ep);      // second pass uses the prefetched weights
   ptx::tc_fence_before();
   __syncthreads();
-  run_event(rg, ep, g2, x_img, w_img, chunks, tmem_base, ctrl, nullptr, g2, 0);
+  run_event(rg, ep, x_img, w_img, chunks, tmem_base, ctrl, nullptr);
   const int row = (quad & 1) * 32 + lane;
   float g[kHiCols / 8][8];
   for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
@@ -1334,7 +1269,7 @@ int selftest_umma(const float* A, const float* W, int N, int K, int passes, floa
   T2_LAUNCH_CHECK();
   pack_rows_image_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
   T2_LAUNCH_CHECK();
-  const size_t smem = (size_t)kStages * kStageBytes + 24 * 8 + 16 + (size_t)kRows * kHiCols * 4 + 64;
+  const size_t smem = (size_t)kStages * kStageBytes + 16 * 8 + 16 + (size_t)kRows * kHiCols * 4 + 64;
   T2_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   selftest_kernel<<<1, kThreads, smem, s>>>(ximg, wimg, ep, chunks, C, N, ctrl);
   T2_LAUNCH_CHECK();
