@@ -1147,11 +1147,15 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
   const size_t smem = persistent_smem_bytes(T);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  int want = 8;
+  // TMA multicast of the activation chunks over clusters (T2_CLUSTER = 2 / 4 / 8) is implemented and
+  // validated, but measured slower than independent fetches on B200 (53.8 vs 55.1 / 56.0 us per step for
+  // cluster 1 / 2 / 4, same box): the stream is latency bound, not L2-bandwidth bound, and the multicast
+  // couples the 4 rings of a cluster in lock step.  Default: no cluster.
+  int want = 1;
   {
-    const char* e = getenv("T2_CLUSTER");      // 1 disables the TMA multicast of the activation stream
+    const char* e = getenv("T2_CLUSTER");
     if (e) want = atoi(e);
-    if (want != 1 && want != 2 && want != 4 && want != 8) want = 8;
+    if (want != 1 && want != 2 && want != 4 && want != 8) want = 1;
   }
   {
     // the hierarchical (cluster barrier + 1 poller per cluster) variant measured slower than the flat
