@@ -298,8 +298,8 @@ def main():
         "decoder_step_us": dec_s / T_MEL * 1e6, "decoder_ms": dec_s * 1e3,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      # dram__bytes_read+write of the persistent kernel from the ncu --set full capture in
-                     # profiles/r01_decoder_v10_ncu_summary.md (3.731 GB per 100-step launch), scaled to 800 steps
-                     "traffic": 3.731e9 * T_MEL / 100, "kernel": "decoder (persistent kernel + processed_memory GEMM), CUDA events",
+                     # profiles/r01_decoder_final_ncu_summary.md (3.796 GB per 100-step launch), scaled to 800 steps
+                     "traffic": 3.796e9 * T_MEL / 100, "kernel": "decoder (persistent kernel + processed_memory GEMM), CUDA events",
                      "peak_source": peak_src, "algorithmic_flop_per_frame": FLOP_PER_FRAME,
                      "stream_bytes": {"achieved_GBps": ach_gbs, "peak_GBps": peak_gbs, "frac": ach_gbs / peak_gbs,
                                       "bytes_per_step": STREAM_BYTES_PER_STEP}},
