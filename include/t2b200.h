@@ -139,9 +139,48 @@ typedef struct T2DecoderArgs {
   float gate_threshold, score_mask_value;
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   void* ws; size_t ws_bytes;
+  void* stash; size_t stash_bytes;     /* TEACHER only, optional: activations kept for t2_decoder_backward
+                                          (t2_decoder_stash_bytes(); opaque to the caller) */
 } T2DecoderArgs;
 size_t t2_decoder_workspace_bytes(const T2Model* m, int32_t B, int32_t T_enc, int32_t n_steps_cap);
 int    t2_decoder_run(T2Model* m, const T2DecoderArgs* a, void* stream);
+
+/* ---- Decoder backward (the autograd graph of Decoder.forward, model.py:381-416) ----------------
+ * Reverse-time recurrence over the stash of a TEACHER run with the same memory / teacher_prenet / masks /
+ * seed, then the time-batched weight gradients.  B <= 64.
+ *   d_mel (B, T_mel, 80), d_gate (B, T_mel): gradients wrt the mel / gate outputs (same layout as the
+ *   outputs); d_align (B, T_mel, T_enc) or NULL.
+ *   d_memory (B, T_enc, 512) and d_prenet (T_mel, B, 256) (gradient wrt teacher_prenet) are written.
+ *   grads: T2_NUM_WEIGHTS pointers in state_dict order; the decoder entries that are non-NULL (attention_rnn,
+ *   attention_layer, decoder_rnn, linear_projection, gate_layer) are OVERWRITTEN with the gradient of the
+ *   corresponding parameter.  The prenet parameters are handled by t2_prenet_backward. */
+typedef struct T2DecoderBwdArgs {
+  const float* memory; const int32_t* memory_lengths; int32_t B, T_enc, T_mel;
+  int32_t training;                    /* same value as the forward call (hidden-state dropout on / off) */
+  const float* teacher_prenet;
+  const uint8_t* att_keep; const uint8_t* dec_keep; uint64_t seed;
+  float score_mask_value;
+  const float* align;                  /* (B, T_mel, T_enc) forward output */
+  const void* stash; size_t stash_bytes;
+  const float* d_mel; const float* d_gate; const float* d_align;
+  float* d_memory; float* d_prenet;
+  float* const* grads; int32_t n_grads;
+  void* ws; size_t ws_bytes;
+} T2DecoderBwdArgs;
+size_t t2_decoder_stash_bytes(const T2Model* m, int32_t B, int32_t T_enc, int32_t T_mel);
+size_t t2_decoder_backward_workspace_bytes(const T2Model* m, int32_t B, int32_t T_enc, int32_t T_mel);
+int    t2_decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, void* stream);
+
+/* Backward of t2_prenet_forward: frames (M, 80), the same keep / seed, d_out (M, 256) ->
+ * grads[prenet.layers.0 / 1] overwritten (d_frames is not needed: the frames are data, model.py:396-399). */
+typedef struct T2PrenetBwdArgs {
+  const float* frames; int32_t M; const uint8_t* keep; uint64_t seed;
+  const float* d_out;
+  float* const* grads; int32_t n_grads;
+  void* ws; size_t ws_bytes;
+} T2PrenetBwdArgs;
+size_t t2_prenet_backward_workspace_bytes(const T2Model* m, int32_t M);
+int    t2_prenet_backward(T2Model* m, const T2PrenetBwdArgs* a, void* stream);
 
 /* Prenet over a block of frames (teacher forcing hoists it out of the loop, model.py:399):
  * frames (M, 80) -> out (M, 256); keep (2, M, 256) uint8 or NULL => Philox(seed). */

@@ -17,6 +17,8 @@ EXPORTS = [
     "t2_decoder_workspace_bytes", "t2_decoder_run", "t2_prenet_forward",
     "t2_postnet_workspace_bytes", "t2_postnet_forward", "t2_infer_workspace_bytes", "t2_infer_host",
     "t2_selftest_umma", "t2_kernel_launch_count", "t2_decoder_profile", "t2_selftest_mma_rate",
+    "t2_decoder_stash_bytes", "t2_decoder_backward_workspace_bytes", "t2_decoder_backward",
+    "t2_prenet_backward_workspace_bytes", "t2_prenet_backward",
 ]
 
 
@@ -45,6 +47,25 @@ class T2DecoderArgs(C.Structure):
                 ("gate_threshold", C.c_float), ("score_mask_value", C.c_float),
                 ("mel", C.c_void_p), ("gate", C.c_void_p), ("align", C.c_void_p),
                 ("mel_lengths", C.c_void_p), ("n_steps", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+                ("stash", C.c_void_p), ("stash_bytes", C.c_size_t)]
+
+
+class T2DecoderBwdArgs(C.Structure):
+    _fields_ = [("memory", C.c_void_p), ("memory_lengths", C.c_void_p),
+                ("B", C.c_int32), ("T_enc", C.c_int32), ("T_mel", C.c_int32), ("training", C.c_int32),
+                ("teacher_prenet", C.c_void_p), ("att_keep", C.c_void_p), ("dec_keep", C.c_void_p),
+                ("seed", C.c_uint64), ("score_mask_value", C.c_float), ("align", C.c_void_p),
+                ("stash", C.c_void_p), ("stash_bytes", C.c_size_t),
+                ("d_mel", C.c_void_p), ("d_gate", C.c_void_p), ("d_align", C.c_void_p),
+                ("d_memory", C.c_void_p), ("d_prenet", C.c_void_p),
+                ("grads", C.POINTER(C.c_void_p)), ("n_grads", C.c_int32),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+class T2PrenetBwdArgs(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("M", C.c_int32), ("keep", C.c_void_p), ("seed", C.c_uint64),
+                ("d_out", C.c_void_p), ("grads", C.POINTER(C.c_void_p)), ("n_grads", C.c_int32),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
@@ -80,12 +101,17 @@ def lib():
     for n in ("t2_encoder_workspace_bytes", "t2_postnet_workspace_bytes"):
         getattr(L, n).restype = C.c_size_t
         getattr(L, n).argtypes = [C.c_void_p, C.c_int32, C.c_int32]
-    for n in ("t2_decoder_workspace_bytes", "t2_infer_workspace_bytes"):
+    for n in ("t2_decoder_workspace_bytes", "t2_infer_workspace_bytes", "t2_decoder_stash_bytes",
+              "t2_decoder_backward_workspace_bytes"):
         getattr(L, n).restype = C.c_size_t
         getattr(L, n).argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     L.t2_encoder_forward.argtypes = [C.c_void_p, C.POINTER(T2EncoderArgs), C.c_void_p]
     L.t2_decoder_run.argtypes = [C.c_void_p, C.POINTER(T2DecoderArgs), C.c_void_p]
     L.t2_postnet_forward.argtypes = [C.c_void_p, C.POINTER(T2PostnetArgs), C.c_void_p]
+    L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]
+    L.t2_prenet_backward.argtypes = [C.c_void_p, C.POINTER(T2PrenetBwdArgs), C.c_void_p]
+    L.t2_prenet_backward_workspace_bytes.restype = C.c_size_t
+    L.t2_prenet_backward_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
     L.t2_prenet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.t2_infer_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,

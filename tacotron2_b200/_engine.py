@@ -209,7 +209,7 @@ class Engine:
     # -- decoder ---------------------------------------------------------------------------------
     def decoder(self, memory, mode, n_steps_cap, memory_lengths=None, teacher_prenet=None, training=False,
                 prenet_keep=None, att_keep=None, dec_keep=None, gate_threshold=0.5,
-                score_mask_value=-float("inf"), impl=None):
+                score_mask_value=-float("inf"), impl=None, stash=None, seed=None):
         L = _capi.lib()
         memory = memory.to(device=self.device, dtype=torch.float32).contiguous()
         B, T = int(memory.shape[0]), int(memory.shape[1])
@@ -237,7 +237,9 @@ class Engine:
         a.prenet_keep = pk.data_ptr() if pk is not None else None
         a.att_keep = ak.data_ptr() if ak is not None else None
         a.dec_keep = dk.data_ptr() if dk is not None else None
-        a.seed = next_seed()
+        a.seed = next_seed() if seed is None else seed
+        if stash is not None:
+            a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
         a.gate_threshold = float(gate_threshold)
         a.score_mask_value = float(score_mask_value)
         a.mel, a.gate, a.align = mel.data_ptr(), gate.data_ptr(), align.data_ptr()
@@ -258,7 +260,75 @@ class Engine:
                  "att:im2col", "att:mma", "att:energies", "att:softmax", "att:context"]
         return {names[i]: [int(out[s * 24 + i]) for s in range(3)] for i in range(len(names))}
 
-    def prenet(self, frames, keep=None):
+    def grad_table(self, named_grads):
+        """(ctypes pointer array of T2_NUM_WEIGHTS entries, held tensors): named_grads maps full state_dict names to
+        the contiguous fp32 tensors the library overwrites with that parameter's gradient."""
+        ptrs = (C.c_void_p * _capi.T2_NUM_WEIGHTS)()
+        for i, (n, _) in enumerate(self.spec):
+            t = named_grads.get(n)
+            ptrs[i] = t.data_ptr() if t is not None else None
+        return ptrs
+
+    def decoder_stash(self, B, T_enc, T_mel):
+        n = _capi.lib().t2_decoder_stash_bytes(self.handle, B, T_enc, T_mel)
+        return torch.empty(int(n), dtype=torch.uint8, device=self.device)
+
+    def decoder_backward(self, memory, memory_lengths, teacher_prenet, align, stash, seed, training, att_keep, dec_keep,
+                         score_mask_value, d_mel, d_gate, d_align, named_grads):
+        """Backward of the teacher-forced decoder run that filled `stash`.  d_mel (B, T, 80), d_gate (B, T), d_align
+        (B, T, T_enc) or None.  Returns (d_memory (B, T_enc, 512), d_prenet (T, B, 256))."""
+        L = _capi.lib()
+        B, Te = int(memory.shape[0]), int(memory.shape[1])
+        T = int(align.shape[1])
+        f32 = dict(device=self.device, dtype=torch.float32)
+        d_memory = torch.empty(B, Te, self.hp.encoder_embedding_dim, **f32)
+        d_prenet = torch.empty(T, B, self.hp.prenet_dim, **f32)
+        ws = self._workspace("dec_bwd", L.t2_decoder_backward_workspace_bytes(self.handle, B, Te, T))
+        a = _capi.T2DecoderBwdArgs()
+        memory = memory.contiguous()
+        a.memory = memory.data_ptr()
+        len32 = None
+        if memory_lengths is not None:
+            len32 = memory_lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            a.memory_lengths = len32.data_ptr()
+        a.B, a.T_enc, a.T_mel, a.training = B, Te, T, int(bool(training))
+        a.teacher_prenet = teacher_prenet.data_ptr()
+        ak, dk = _u8(att_keep, self.device), _u8(dec_keep, self.device)
+        a.att_keep = ak.data_ptr() if ak is not None else None
+        a.dec_keep = dk.data_ptr() if dk is not None else None
+        a.seed, a.score_mask_value = seed, float(score_mask_value)
+        a.align, a.stash, a.stash_bytes = align.data_ptr(), stash.data_ptr(), stash.numel()
+        d_mel, d_gate = d_mel.to(**f32).contiguous(), d_gate.to(**f32).contiguous()
+        a.d_mel, a.d_gate = d_mel.data_ptr(), d_gate.data_ptr()
+        if d_align is not None:
+            d_align = d_align.to(**f32).contiguous()
+            a.d_align = d_align.data_ptr()
+        a.d_memory, a.d_prenet = d_memory.data_ptr(), d_prenet.data_ptr()
+        ptrs = self.grad_table(named_grads)
+        a.grads, a.n_grads = ptrs, _capi.T2_NUM_WEIGHTS
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(self.device):
+            _capi.check(L.t2_decoder_backward(self.handle, C.byref(a), self._stream()))
+        return d_memory, d_prenet
+
+    def prenet_backward(self, frames, keep, seed, d_out, named_grads):
+        L = _capi.lib()
+        frames = frames.to(device=self.device, dtype=torch.float32).contiguous()
+        M = int(frames.shape[0])
+        d_out = d_out.contiguous()
+        ws = self._workspace("pre_bwd", L.t2_prenet_backward_workspace_bytes(self.handle, M))
+        keep = _u8(keep, self.device)
+        a = _capi.T2PrenetBwdArgs()
+        a.frames, a.M = frames.data_ptr(), M
+        a.keep = keep.data_ptr() if keep is not None else None
+        a.seed, a.d_out = seed, d_out.data_ptr()
+        ptrs = self.grad_table(named_grads)
+        a.grads, a.n_grads = ptrs, _capi.T2_NUM_WEIGHTS
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(self.device):
+            _capi.check(L.t2_prenet_backward(self.handle, C.byref(a), self._stream()))
+
+    def prenet(self, frames, keep=None, seed=None):
         """frames (M, 80) -> (M, 256); keep (2, M, 256) uint8 or None."""
         L = _capi.lib()
         frames = frames.to(device=self.device, dtype=torch.float32).contiguous()
@@ -268,7 +338,8 @@ class Engine:
         keep = _u8(keep, self.device)
         with torch.cuda.device(self.device):
             _capi.check(L.t2_prenet_forward(self.handle, frames.data_ptr(), M,
-                                            keep.data_ptr() if keep is not None else None, next_seed(),
+                                            keep.data_ptr() if keep is not None else None,
+                                            next_seed() if seed is None else seed,
                                             out.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return out
 

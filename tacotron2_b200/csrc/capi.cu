@@ -229,6 +229,7 @@ int t2_model_destroy(T2Model* m) {
   for (int i = 0; i < 5; ++i) cudaFree(m->tc_post_conv[i]);
   cudaFree(m->tc_enc_wih);
   persistent_pack_destroy(m);
+  blas_destroy(m);
   delete m;
   return T2_OK;
 }
@@ -249,6 +250,22 @@ int t2_decoder_run(T2Model* m, const T2DecoderArgs* a, void* stream) {
     return decoder_run_persistent(m, a, (cudaStream_t)stream);
   }
   return decoder_run_stepwise(m, a, (cudaStream_t)stream);
+}
+
+size_t t2_decoder_stash_bytes(const T2Model*, int32_t B, int32_t, int32_t T_mel) { return decoder_stash_bytes(B, T_mel); }
+size_t t2_decoder_backward_workspace_bytes(const T2Model*, int32_t B, int32_t T_enc, int32_t T_mel) {
+  return decoder_backward_ws_bytes(B, T_enc, T_mel);
+}
+int t2_decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, void* stream) {
+  if (!m || !a || !a->memory || !a->teacher_prenet || !a->align || !a->stash || !a->d_mel || !a->d_gate || !a->d_prenet ||
+      !a->grads || !a->ws)
+    return fail(T2_ERR_INVALID, "decoder backward: null argument");
+  return decoder_backward(m, a, (cudaStream_t)stream);
+}
+size_t t2_prenet_backward_workspace_bytes(const T2Model*, int32_t M) { return (size_t)4 * M * kPre * 4 + 1024; }
+int t2_prenet_backward(T2Model* m, const T2PrenetBwdArgs* a, void* stream) {
+  if (!m || !a || !a->frames || !a->d_out || !a->grads || !a->ws || a->M <= 0) return fail(T2_ERR_INVALID, "prenet backward: bad argument");
+  return prenet_backward(m, a, (cudaStream_t)stream);
 }
 
 int t2_prenet_forward(T2Model* m, const float* frames, int32_t M, const uint8_t* keep, uint64_t seed, float* out,

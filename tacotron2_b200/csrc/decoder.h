@@ -30,11 +30,36 @@ struct DecoderWs {
   char* persistent; size_t persistent_bytes;  // extra region used by the persistent kernel
 };
 
+// Training stash written by the persistent kernel in teacher-forced mode and read by the backward pass
+// (decoder_backward.cu).  All fp32, step-major.  h = the hidden state that recurs (after dropout).
+struct DecoderStash {
+  float* ga = nullptr; float* gd = nullptr;                   // (T, B, 4096) gate activations i | f | g | o
+  float* ca = nullptr; float* ha = nullptr;                   // (T + 1, B, 1024), slot 0 = initial zeros
+  float* cd = nullptr; float* hd = nullptr;
+  float* ctx = nullptr;                                       // (T + 1, B, 512), slot 0 = zeros
+};
+inline size_t decoder_stash_bytes(int B, int T) {
+  return ((size_t)2 * T * B * 4096 + (size_t)4 * (T + 1) * B * 1024 + (size_t)(T + 1) * B * 512) * sizeof(float);
+}
+inline void decoder_stash_carve(void* base, int B, int T, DecoderStash* s) {
+  float* f = (float*)base;
+  s->ga = f; f += (size_t)T * B * 4096;
+  s->gd = f; f += (size_t)T * B * 4096;
+  s->ca = f; f += (size_t)(T + 1) * B * 1024;
+  s->ha = f; f += (size_t)(T + 1) * B * 1024;
+  s->cd = f; f += (size_t)(T + 1) * B * 1024;
+  s->hd = f; f += (size_t)(T + 1) * B * 1024;
+  s->ctx = f;
+}
+
 size_t decoder_ws_bytes(int B, int T, int cap);
 size_t persistent_ws_bytes(int B, int T, int cap);
 int decoder_ws_carve(const T2DecoderArgs* a, DecoderWs* w);
 int decoder_run_stepwise(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);
 int decoder_run_persistent(T2Model* m, const T2DecoderArgs* a, cudaStream_t s);
+int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s);
+size_t decoder_backward_ws_bytes(int B, int T_enc, int T_mel);
+int prenet_backward(T2Model* m, const T2PrenetBwdArgs* a, cudaStream_t s);
 bool persistent_supported(const T2Model* m, const T2DecoderArgs* a);
 
 }  // namespace t2

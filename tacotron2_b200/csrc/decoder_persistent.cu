@@ -406,6 +406,18 @@ __device__ __forceinline__ void acc_take8(uint32_t t_lane, int base, int n, int 
   ptx::tmem_wait_st();
 }
 
+// training stash (decoder.h DecoderStash): gate activations, cell state and (post-dropout) hidden state of
+// units [unit0, unit0 + 2) of batch row b at step t, fp32, PyTorch gate order
+__device__ __forceinline__ void stash_lstm(float* gates, float* cs, float* hs, int t, int Btot, int b, int unit0,
+                                           const float (&sg)[4][2], const float (&c)[2], const float (&h)[2]) {
+  float* gp = gates + ((long)t * Btot + b) * (4 * kARnn) + unit0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(gp + g * kARnn) = make_float2(sg[g][0], sg[g][1]);
+  const long o = ((long)(t + 1) * Btot + b) * kARnn + unit0;
+  *reinterpret_cast<float2*>(cs + o) = make_float2(c[0], c[1]);
+  *reinterpret_cast<float2*>(hs + o) = make_float2(h[0], h[1]);
+}
+
 struct KParams {
   const CtaPlan* plans;
   const uint8_t* wimg;
@@ -425,6 +437,7 @@ struct KParams {
   int b0, Btot;                     // this launch handles batch rows [b0, b0 + B) of Btot (dropout mask / Philox indexing)
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
+  DecoderStash st;                  // training stash for the backward pass (st.ga == nullptr: none)
 };
 
 __device__ __forceinline__ void store_split2(uint8_t* img, int row, int k, float v0, float v1) {
@@ -558,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       float g[8];
       T2_TAKE_GATES(kColA, kNA, g);
       if (erow) {
-        float hv[2];
+        float hv[2], sg[4][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const float* b = s_bias_a + (cg * 2 + u) * 4;
@@ -576,8 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
             h = keep ? h * (1.f / (1.f - p.p_att)) : 0.f;
           }
           hv[u] = h;
+          sg[0][u] = gi; sg[1][u] = gf; sg[2][u] = gg; sg[3][u] = go;
         }
         store_split2(p.ah_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
+        if (p.st.ga) stash_lstm(p.st.ga, p.st.ca, p.st.ha, t, p.Btot, p.b0 + row, cta * 8 + cg * 2, sg, c_att, hv);
       }
       T2_PROF(1);
       grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B1: ah_t complete
@@ -810,6 +825,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 #pragma unroll
           for (int g = 0; g < 8; ++g) { v0 += scr[g * (kEnc / 2) + col]; v1 += scr[g * (kEnc / 2) + col + 1]; }
           store_split2(p.ctx_img, b, ahalf * (kEnc / 2) + col, v0, v1);
+          if (p.st.ga)
+            *reinterpret_cast<float2*>(p.st.ctx + ((long)(t + 1) * p.Btot + p.b0 + b) * kEnc + ahalf * (kEnc / 2) + col) =
+                make_float2(v0, v1);
         }
       }
       T2_PROF(19);
@@ -824,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       float g[8];
       T2_TAKE_GATES(kColD, kND, g);
       if (erow) {
-        float hv[2];
+        float hv[2], sg[4][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const float* b = s_bias_d + (cg * 2 + u) * 4;
@@ -842,8 +860,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
             h = keep ? h * (1.f / (1.f - p.p_dec)) : 0.f;
           }
           hv[u] = h;
+          sg[0][u] = gi; sg[1][u] = gf; sg[2][u] = gg; sg[3][u] = go;
         }
         store_split2(p.dh_img, row, cta * 8 + cg * 2, hv[0], hv[1]);
+        if (p.st.ga) stash_lstm(p.st.gd, p.st.cd, p.st.hd, t, p.Btot, p.b0 + row, cta * 8 + cg * 2, sg, c_dec, hv);
       }
       T2_PROF(8);
       grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B4: dh_t complete
@@ -1134,6 +1154,16 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
   p.B = B; p.T = T; p.cap = cap; p.infer = a->mode == T2_MODE_INFER; p.training = a->training;
   p.gate_threshold = a->gate_threshold; p.score_mask_value = a->score_mask_value;
   p.p_att = m->cfg.p_attention_dropout; p.p_dec = m->cfg.p_decoder_dropout; p.seed = a->seed;
+  if (a->stash) {
+    if (p.infer) return fail(T2_ERR_INVALID, "the training stash needs T2_MODE_TEACHER");
+    if (a->stash_bytes < decoder_stash_bytes(a->B, cap)) return fail(T2_ERR_WORKSPACE, "decoder stash too small");
+    decoder_stash_carve(a->stash, a->B, cap, &p.st);
+    if (b0 == 0) {   // slot 0 of the recurrent states = the zero initial states (model.py:258-284)
+      float* z[5] = {p.st.ca, p.st.ha, p.st.cd, p.st.hd, p.st.ctx};
+      for (int i = 0; i < 5; ++i)
+        T2_CUDA(cudaMemsetAsync(z[i], 0, (size_t)a->B * (i < 4 ? kARnn : kEnc) * sizeof(float), s));
+    }
+  }
   if (!p.infer) {
     // teacher forcing (model.py:396-405): the prenet outputs of all steps are known up front -> convert
     // them once into x2 operand images, the kernel then skips the prenet events and their two barriers

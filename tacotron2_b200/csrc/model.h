@@ -26,10 +26,12 @@ struct T2Model {
 
   // ---- packed operands of the persistent decoder kernel (owned; see decoder_persistent.cu) ----
   void* pk = nullptr;            // opaque PersistentPack*
+  void* blas = nullptr;          // cublasHandle_t of the backward pass (time-batched plain GEMMs), created lazily
 };
 
 namespace t2 {
 int pack_model(T2Model* m, cudaStream_t s);          // (re)builds every packed copy
 int persistent_pack_create(T2Model* m, cudaStream_t s);
 void persistent_pack_destroy(T2Model* m);
+void blas_destroy(T2Model* m);
 }  // namespace t2

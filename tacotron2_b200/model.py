@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import _capi
-from ._engine import Engine, current_masks
+from ._engine import Engine, current_masks, next_seed
 from .layers import ConvNorm, LinearNorm
 from .utils import get_mask_from_lengths, to_gpu
 
@@ -234,25 +234,41 @@ class Decoder(nn.Module, _EngineOwner):
                                              int(decoder_inputs.size(1) / self.n_frames_per_step), -1)
         return decoder_inputs.transpose(0, 1)
 
-    def forward(self, memory, decoder_inputs, memory_lengths):
-        """Teacher-forced pass (model.py:381-416).  Returns mel (B, n_mel, T), gate (B, T),
-        alignments (B, T, T_enc)."""
-        _require_no_grad(self, "Decoder.forward")
+    def _teacher_forward(self, memory, decoder_inputs, memory_lengths, keep_stash):
+        """Shared by the no-grad path and _DecoderFn.forward.  Returns (mel (B,T,80), gate, align, saved)."""
         eng = self._t2_engine()
         masks = current_masks()
-        B = memory.size(0)
         go = self.get_go_frame(memory).unsqueeze(0)
         frames = torch.cat((go.float(), self.parse_decoder_inputs(decoder_inputs).float()), dim=0)   # (T+1, B, 80)
         T_mel = frames.size(0) - 1
         pk = masks["prenet"]
         if pk is not None:
             pk = pk.permute(1, 0, 2, 3).reshape(2, -1, pk.shape[-1])
-        px = eng.prenet(frames.reshape(-1, frames.size(-1)), pk)                                     # model.py:399
+        frames2d = frames.reshape(-1, frames.size(-1))
+        pre_seed, dec_seed = next_seed(), next_seed()
+        px = eng.prenet(frames2d, pk, seed=pre_seed)                                                 # model.py:399
         smv = float(self.attention_layer.score_mask_value)
+        mem32 = memory.detach().to(dtype=torch.float32).contiguous()
+        stash = eng.decoder_stash(mem32.size(0), mem32.size(1), T_mel) if keep_stash else None
         mel, gate, align, _, _ = eng.decoder(
-            memory, _capi.MODE_TEACHER, T_mel, memory_lengths=memory_lengths, teacher_prenet=px,
-            training=self.training, att_keep=masks["att"], dec_keep=masks["dec"], score_mask_value=smv)
+            mem32, _capi.MODE_TEACHER, T_mel, memory_lengths=memory_lengths, teacher_prenet=px,
+            training=self.training, att_keep=masks["att"], dec_keep=masks["dec"], score_mask_value=smv,
+            stash=stash, seed=dec_seed)
+        saved = dict(eng=eng, memory=mem32, memory_lengths=memory_lengths, frames=frames2d, pk=pk, px=px, align=align,
+                     stash=stash, pre_seed=pre_seed, dec_seed=dec_seed, training=self.training, att_keep=masks["att"],
+                     dec_keep=masks["dec"], smv=smv)
+        return mel, gate, align, saved
+
+    def forward(self, memory, decoder_inputs, memory_lengths):
+        """Teacher-forced pass (model.py:381-416).  Returns mel (B, n_mel, T), gate (B, T),
+        alignments (B, T, T_enc).  Under autograd the backward pass is libt2b200's hand-written reverse
+        recurrence (t2_decoder_backward / t2_prenet_backward)."""
         dt = memory.dtype
+        params = [p_ for p_ in self.parameters()]
+        if torch.is_grad_enabled() and (memory.requires_grad or any(p_.requires_grad for p_ in params)):
+            mel, gate, align = _DecoderFn.apply(self, memory, decoder_inputs, memory_lengths, *params)
+        else:
+            mel, gate, align, _ = self._teacher_forward(memory, decoder_inputs, memory_lengths, False)
         return mel.transpose(1, 2).to(dt), gate.to(dt), align.to(dt)
 
     def inference(self, memory):
@@ -271,6 +287,42 @@ class Decoder(nn.Module, _EngineOwner):
                 print("Warning! Reached max decoder steps")                                         # model.py:446
         dt = memory.dtype
         return (mel[:, :n].transpose(1, 2).to(dt), gate[:, :n].unsqueeze(-1).to(dt), align[:, :n].to(dt))
+
+
+class _DecoderFn(torch.autograd.Function):
+    """Decoder.forward (model.py:381-416) as one autograd node: forward = the persistent teacher-forced kernel with
+    its training stash, backward = t2_decoder_backward + t2_prenet_backward."""
+
+    @staticmethod
+    def forward(ctx, dec, memory, decoder_inputs, memory_lengths, *params):
+        mel, gate, align, saved = dec._teacher_forward(memory, decoder_inputs, memory_lengths, True)
+        ctx.dec, ctx.saved = dec, saved
+        ctx.mem_dtype = memory.dtype
+        ctx.set_materialize_grads(False)
+        return mel, gate, align
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_mel, d_gate, d_align):
+        sv, dec = ctx.saved, ctx.dec
+        eng = sv["eng"]
+        align = sv["align"]
+        B, T = align.shape[0], align.shape[1]
+        f32 = dict(device=align.device, dtype=torch.float32)
+        if d_mel is None:
+            d_mel = torch.zeros(B, T, dec.n_mel_channels, **f32)
+        if d_gate is None:
+            d_gate = torch.zeros(B, T, **f32)
+        named = [("decoder." + k, p_) for k, p_ in dec.named_parameters()]
+        grads = {n: torch.empty(p_.shape, **f32) for n, p_ in named}
+        d_memory, d_px = eng.decoder_backward(
+            sv["memory"], sv["memory_lengths"], sv["px"], align, sv["stash"], sv["dec_seed"], sv["training"],
+            sv["att_keep"], sv["dec_keep"], sv["smv"], d_mel, d_gate, d_align, grads)
+        # the prenet ran over T+1 frames (model.py:396-399); the last frame's output is unused (model.py:405)
+        d_out = torch.cat((d_px.reshape(-1, d_px.shape[-1]), torch.zeros(B, d_px.shape[-1], **f32)), 0)
+        eng.prenet_backward(sv["frames"], sv["pk"], sv["pre_seed"], d_out, grads)
+        ctx.saved = None
+        return (None, d_memory.to(ctx.mem_dtype), None, None) + tuple(grads[n].to(p_.dtype) for n, p_ in named)
 
 
 class Tacotron2(nn.Module, _EngineOwner):

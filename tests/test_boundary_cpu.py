@@ -97,7 +97,12 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         "T2EncoderArgs": ["text", "embedded", "lengths", "B", "T", "training", "keep", "seed", "memory", "ws", "ws_bytes"],
         "T2DecoderArgs": ["mode", "impl", "training", "memory", "memory_lengths", "B", "T_enc", "n_steps_cap",
                           "teacher_prenet", "prenet_keep", "att_keep", "dec_keep", "seed", "gate_threshold",
-                          "score_mask_value", "mel", "gate", "align", "mel_lengths", "n_steps", "ws", "ws_bytes"],
+                          "score_mask_value", "mel", "gate", "align", "mel_lengths", "n_steps", "ws", "ws_bytes",
+                          "stash", "stash_bytes"],
+        "T2DecoderBwdArgs": ["memory", "memory_lengths", "B", "T_enc", "T_mel", "training", "teacher_prenet", "att_keep",
+                             "dec_keep", "seed", "score_mask_value", "align", "stash", "stash_bytes", "d_mel", "d_gate",
+                             "d_align", "d_memory", "d_prenet", "grads", "n_grads", "ws", "ws_bytes"],
+        "T2PrenetBwdArgs": ["frames", "M", "keep", "seed", "d_out", "grads", "n_grads", "ws", "ws_bytes"],
         "T2PostnetArgs": ["mel", "mel_batch_stride", "lengths", "B", "T", "training", "keep", "seed",
                           "add_residual", "mel_post", "ws", "ws_bytes"],
     }
