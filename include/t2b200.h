@@ -110,9 +110,27 @@ typedef struct T2EncoderArgs {
   int32_t training; const uint8_t* keep; uint64_t seed;
   float* memory;                       /* out (B, T, 512) */
   void* ws; size_t ws_bytes;
+  void* stash; size_t stash_bytes;     /* optional: activations kept for t2_encoder_backward (B <= 64) */
 } T2EncoderArgs;
 size_t t2_encoder_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
 int    t2_encoder_forward(T2Model* m, const T2EncoderArgs* a, void* stream);
+
+/* Encoder backward (autograd graph of Encoder.forward, model.py:173-190): the stash of a forward call with the same
+ * text / embedded, lengths, training, keep and seed; d_memory (B, T, 512) -> gradients of the encoder parameters
+ * (grads[] entries that are non-NULL are overwritten; with `text` also embedding.weight) and, if non-NULL,
+ * d_embedded (B, T, 512). */
+typedef struct T2EncoderBwdArgs {
+  const int64_t* text; const float* embedded; const int32_t* lengths; int32_t B, T;
+  int32_t training; const uint8_t* keep; uint64_t seed;
+  const void* stash; size_t stash_bytes;
+  const float* d_memory;
+  float* d_embedded;
+  float* const* grads; int32_t n_grads;
+  void* ws; size_t ws_bytes;
+} T2EncoderBwdArgs;
+size_t t2_encoder_stash_bytes(const T2Model* m, int32_t B, int32_t T);
+size_t t2_encoder_backward_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
+int    t2_encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, void* stream);
 
 /* ---- Decoder (model.py:204-454) --------------------------------------------------------------
  * One call runs the whole autoregressive loop.
@@ -200,9 +218,27 @@ typedef struct T2PostnetArgs {
   int32_t add_residual;                /* 1: mel_post = mel^T + postnet(mel^T) (model.py:511, 524); 0: postnet only */
   float* mel_post;
   void* ws; size_t ws_bytes;
+  void* stash; size_t stash_bytes;     /* optional (lengths must be NULL): activations kept for t2_postnet_backward */
 } T2PostnetArgs;
 size_t t2_postnet_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
 int    t2_postnet_forward(T2Model* m, const T2PostnetArgs* a, void* stream);
+
+/* Postnet backward (model.py:141-146 + the residual of :511): d_mel_post (B, 80, T) -> d_mel (B, T, 80) (gradient wrt
+ * the input rows, including the residual branch when add_residual) and the postnet parameter gradients. */
+typedef struct T2PostnetBwdArgs {
+  int32_t B, T, training, add_residual; const uint8_t* keep; uint64_t seed;
+  const int32_t* wgrad_lengths;        /* (B) or NULL: frames t >= wgrad_lengths[b] of the stashed INPUT count as zero in the
+                                          first conv's weight gradient -- what the reference's autograd computes, because
+                                          parse_output zeroes that tensor in place after the forward pass (model.py:492) */
+  const void* stash; size_t stash_bytes;
+  const float* d_mel_post;
+  float* d_mel;
+  float* const* grads; int32_t n_grads;
+  void* ws; size_t ws_bytes;
+} T2PostnetBwdArgs;
+size_t t2_postnet_stash_bytes(const T2Model* m, int32_t B, int32_t T);
+size_t t2_postnet_backward_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
+int    t2_postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, void* stream);
 
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,

@@ -19,6 +19,8 @@ EXPORTS = [
     "t2_selftest_umma", "t2_kernel_launch_count", "t2_decoder_profile", "t2_selftest_mma_rate",
     "t2_decoder_stash_bytes", "t2_decoder_backward_workspace_bytes", "t2_decoder_backward",
     "t2_prenet_backward_workspace_bytes", "t2_prenet_backward",
+    "t2_encoder_stash_bytes", "t2_encoder_backward_workspace_bytes", "t2_encoder_backward",
+    "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
 ]
 
 
@@ -35,7 +37,15 @@ class T2Config(C.Structure):
 class T2EncoderArgs(C.Structure):
     _fields_ = [("text", C.c_void_p), ("embedded", C.c_void_p), ("lengths", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32),
                 ("training", C.c_int32), ("keep", C.c_void_p), ("seed", C.c_uint64),
-                ("memory", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("memory", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+                ("stash", C.c_void_p), ("stash_bytes", C.c_size_t)]
+
+
+class T2EncoderBwdArgs(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("embedded", C.c_void_p), ("lengths", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32),
+                ("training", C.c_int32), ("keep", C.c_void_p), ("seed", C.c_uint64),
+                ("stash", C.c_void_p), ("stash_bytes", C.c_size_t), ("d_memory", C.c_void_p), ("d_embedded", C.c_void_p),
+                ("grads", C.POINTER(C.c_void_p)), ("n_grads", C.c_int32), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
 class T2DecoderArgs(C.Structure):
@@ -73,7 +83,15 @@ class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
                 ("seed", C.c_uint64), ("add_residual", C.c_int32), ("mel_post", C.c_void_p), ("ws", C.c_void_p),
-                ("ws_bytes", C.c_size_t)]
+                ("ws_bytes", C.c_size_t), ("stash", C.c_void_p), ("stash_bytes", C.c_size_t)]
+
+
+class T2PostnetBwdArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("add_residual", C.c_int32),
+                ("keep", C.c_void_p), ("seed", C.c_uint64), ("wgrad_lengths", C.c_void_p),
+                ("stash", C.c_void_p), ("stash_bytes", C.c_size_t),
+                ("d_mel_post", C.c_void_p), ("d_mel", C.c_void_p),
+                ("grads", C.POINTER(C.c_void_p)), ("n_grads", C.c_int32), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
 _lib = None
@@ -98,7 +116,8 @@ def lib():
                                   C.c_int32, C.c_void_p]
     L.t2_model_refresh.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
     L.t2_model_destroy.argtypes = [C.c_void_p]
-    for n in ("t2_encoder_workspace_bytes", "t2_postnet_workspace_bytes"):
+    for n in ("t2_encoder_workspace_bytes", "t2_postnet_workspace_bytes", "t2_encoder_stash_bytes",
+              "t2_encoder_backward_workspace_bytes", "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes"):
         getattr(L, n).restype = C.c_size_t
         getattr(L, n).argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     for n in ("t2_decoder_workspace_bytes", "t2_infer_workspace_bytes", "t2_decoder_stash_bytes",
@@ -108,6 +127,8 @@ def lib():
     L.t2_encoder_forward.argtypes = [C.c_void_p, C.POINTER(T2EncoderArgs), C.c_void_p]
     L.t2_decoder_run.argtypes = [C.c_void_p, C.POINTER(T2DecoderArgs), C.c_void_p]
     L.t2_postnet_forward.argtypes = [C.c_void_p, C.POINTER(T2PostnetArgs), C.c_void_p]
+    L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
+    L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]
     L.t2_prenet_backward.argtypes = [C.c_void_p, C.POINTER(T2PrenetBwdArgs), C.c_void_p]
     L.t2_prenet_backward_workspace_bytes.restype = C.c_size_t

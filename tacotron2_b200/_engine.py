@@ -180,7 +180,7 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- encoder ---------------------------------------------------------------------------------
-    def encoder(self, text=None, embedded=None, lengths=None, training=False, keep=None):
+    def encoder(self, text=None, embedded=None, lengths=None, training=False, keep=None, stash=None, seed=None):
         L = _capi.lib()
         src = text if text is not None else embedded
         B, T = int(src.shape[0]), int(src.shape[1])
@@ -200,11 +200,77 @@ class Engine:
         keep = _u8(keep, self.device)
         a.B, a.T, a.training = B, T, int(bool(training))
         a.keep = keep.data_ptr() if keep is not None else None
-        a.seed = next_seed()
+        a.seed = next_seed() if seed is None else seed
         a.memory, a.ws, a.ws_bytes = memory.data_ptr(), ws.data_ptr(), ws.numel()
+        if stash is not None:
+            a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
         with torch.cuda.device(self.device):
             _capi.check(L.t2_encoder_forward(self.handle, C.byref(a), self._stream()))
         return memory
+
+    def stash_buffer(self, kind, *dims):
+        n = getattr(_capi.lib(), "t2_%s_stash_bytes" % kind)(self.handle, *dims)
+        return torch.empty(int(n), dtype=torch.uint8, device=self.device)
+
+    def encoder_backward(self, text, embedded, lengths, training, keep, seed, stash, d_memory, want_d_embedded, named_grads):
+        L = _capi.lib()
+        B, T = int(d_memory.shape[0]), int(d_memory.shape[1])
+        f32 = dict(device=self.device, dtype=torch.float32)
+        a = _capi.T2EncoderBwdArgs()
+        if text is not None:
+            text = text.to(device=self.device, dtype=torch.int64).contiguous()
+            a.text = text.data_ptr()
+        else:
+            embedded = embedded.to(**f32).contiguous()
+            a.embedded = embedded.data_ptr()
+        len32 = None
+        if lengths is not None:
+            len32 = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            a.lengths = len32.data_ptr()
+        keep = _u8(keep, self.device)
+        a.B, a.T, a.training = B, T, int(bool(training))
+        a.keep = keep.data_ptr() if keep is not None else None
+        a.seed = seed
+        a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
+        d_memory = d_memory.to(**f32).contiguous()
+        a.d_memory = d_memory.data_ptr()
+        d_emb = torch.empty(B, T, self.hp.encoder_embedding_dim, **f32) if want_d_embedded else None
+        a.d_embedded = d_emb.data_ptr() if d_emb is not None else None
+        ptrs = self.grad_table(named_grads)
+        a.grads, a.n_grads = ptrs, _capi.T2_NUM_WEIGHTS
+        ws = self._workspace("enc_bwd", L.t2_encoder_backward_workspace_bytes(self.handle, B, T))
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(self.device):
+            _capi.check(L.t2_encoder_backward(self.handle, C.byref(a), self._stream()))
+        return d_emb
+
+    def postnet_backward(self, B, T, training, add_residual, keep, seed, stash, d_mel_post, named_grads, wgrad_lengths=None):
+        """d_mel_post (B, 80, T) -> d_mel (B, T, 80)."""
+        L = _capi.lib()
+        f32 = dict(device=self.device, dtype=torch.float32)
+        a = _capi.T2PostnetBwdArgs()
+        a.B, a.T, a.training, a.add_residual = B, T, int(bool(training)), int(bool(add_residual))
+        if keep is not None and isinstance(keep, (list, tuple)):
+            keep = torch.cat([k.to(torch.uint8).reshape(-1) for k in keep])
+        keep = _u8(keep, self.device)
+        a.keep = keep.data_ptr() if keep is not None else None
+        a.seed = seed
+        wl32 = None
+        if wgrad_lengths is not None:
+            wl32 = wgrad_lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            a.wgrad_lengths = wl32.data_ptr()
+        a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
+        d_mel_post = d_mel_post.to(**f32).contiguous()
+        a.d_mel_post = d_mel_post.data_ptr()
+        d_mel = torch.empty(B, T, self.hp.n_mel_channels, **f32)
+        a.d_mel = d_mel.data_ptr()
+        ptrs = self.grad_table(named_grads)
+        a.grads, a.n_grads = ptrs, _capi.T2_NUM_WEIGHTS
+        ws = self._workspace("post_bwd", L.t2_postnet_backward_workspace_bytes(self.handle, B, T))
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(self.device):
+            _capi.check(L.t2_postnet_backward(self.handle, C.byref(a), self._stream()))
+        return d_mel
 
     # -- decoder ---------------------------------------------------------------------------------
     def decoder(self, memory, mode, n_steps_cap, memory_lengths=None, teacher_prenet=None, training=False,
@@ -270,8 +336,7 @@ class Engine:
         return ptrs
 
     def decoder_stash(self, B, T_enc, T_mel):
-        n = _capi.lib().t2_decoder_stash_bytes(self.handle, B, T_enc, T_mel)
-        return torch.empty(int(n), dtype=torch.uint8, device=self.device)
+        return self.stash_buffer("decoder", B, T_enc, T_mel)
 
     def decoder_backward(self, memory, memory_lengths, teacher_prenet, align, stash, seed, training, att_keep, dec_keep,
                          score_mask_value, d_mel, d_gate, d_align, named_grads):
@@ -344,7 +409,7 @@ class Engine:
         return out
 
     # -- postnet ---------------------------------------------------------------------------------
-    def postnet(self, mel_btc, lengths=None, add_residual=True, training=False, keep=None):
+    def postnet(self, mel_btc, lengths=None, add_residual=True, training=False, keep=None, stash=None, seed=None):
         """mel_btc: (B, T, 80) time-major rows (batch stride may exceed T*80).  Returns (B, 80, T)."""
         L = _capi.lib()
         assert mel_btc.dtype == torch.float32 and mel_btc.stride(2) == 1 and mel_btc.stride(1) == mel_btc.shape[2]
@@ -362,9 +427,11 @@ class Engine:
             keep = torch.cat([k.to(torch.uint8).reshape(-1) for k in keep])
         keep = _u8(keep, self.device)
         a.keep = keep.data_ptr() if keep is not None else None
-        a.seed = next_seed()
+        a.seed = next_seed() if seed is None else seed
         a.add_residual = int(bool(add_residual))
         a.mel_post, a.ws, a.ws_bytes = out.data_ptr(), ws.data_ptr(), ws.numel()
+        if stash is not None:
+            a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
         with torch.cuda.device(self.device):
             _capi.check(L.t2_postnet_forward(self.handle, C.byref(a), self._stream()))
         return out

@@ -5,6 +5,7 @@
 #include "conv_tc.h"
 #include "decoder.h"
 #include "gemm_f32.cuh"
+#include "train_layers.h"
 
 namespace t2 {
 
@@ -240,6 +241,20 @@ int t2_encoder_forward(T2Model* m, const T2EncoderArgs* a, void* stream) {
   return encoder_forward(m, a, (cudaStream_t)stream);
 }
 
+size_t t2_encoder_stash_bytes(const T2Model*, int32_t B, int32_t T) { return encoder_stash_bytes(B, T); }
+size_t t2_encoder_backward_workspace_bytes(const T2Model*, int32_t B, int32_t T) { return encoder_backward_ws_bytes(B, T); }
+int t2_encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, void* stream) {
+  if (!m || !a || (!a->text && !a->embedded) || !a->stash || !a->d_memory || !a->grads || !a->ws)
+    return fail(T2_ERR_INVALID, "encoder backward: null argument");
+  return encoder_backward(m, a, (cudaStream_t)stream);
+}
+size_t t2_postnet_stash_bytes(const T2Model*, int32_t B, int32_t T) { return postnet_stash_bytes(B, T); }
+size_t t2_postnet_backward_workspace_bytes(const T2Model*, int32_t B, int32_t T) { return postnet_backward_ws_bytes(B, T); }
+int t2_postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, void* stream) {
+  if (!m || !a || !a->stash || !a->d_mel_post || !a->grads || !a->ws) return fail(T2_ERR_INVALID, "postnet backward: null argument");
+  return postnet_backward(m, a, (cudaStream_t)stream);
+}
+
 size_t t2_decoder_workspace_bytes(const T2Model*, int32_t B, int32_t T_enc, int32_t cap) { return decoder_ws_bytes(B, T_enc, cap); }
 int t2_decoder_run(T2Model* m, const T2DecoderArgs* a, void* stream) {
   T2_TRY(check_decoder_args(m, a));
@@ -288,6 +303,7 @@ int t2_prenet_forward(T2Model* m, const float* frames, int32_t M, const uint8_t*
 size_t t2_postnet_workspace_bytes(const T2Model*, int32_t B, int32_t T) { return postnet_ws_bytes(B, T); }
 int t2_postnet_forward(T2Model* m, const T2PostnetArgs* a, void* stream) {
   if (!m || !a || !a->mel || !a->mel_post || !a->ws) return fail(T2_ERR_INVALID, "postnet: null argument");
+  if (a->stash) return postnet_forward_train(m, a, (cudaStream_t)stream);
   return postnet_forward(m, a, (cudaStream_t)stream);
 }
 

@@ -20,6 +20,30 @@
 
 namespace t2 {
 
+// ---- cuBLAS plumbing (plain time-batched GEMMs) ------------------------------------------------
+int blas_handle(T2Model* m, cudaStream_t s, cublasHandle_t* out) {
+  if (!m->blas) {
+    cublasHandle_t h;
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasCreate failed");
+    const char* e = getenv("T2_WGRAD_TF32");
+    cublasSetMathMode(h, (e && atoi(e)) ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH);
+    m->blas = h;
+  }
+  *out = (cublasHandle_t)m->blas;
+  if (cublasSetStream(*out, s) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSetStream failed");
+  return T2_OK;
+}
+// row-major C (M x N) = op(A) . op(B) + beta C;  ta: A is stored (K x M);  tb: B is stored (N x K)
+int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+            float* C, long ldc, float beta) {
+  const float alpha = 1.f;
+  cublasStatus_t st = cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B,
+                                  (int)ldb, A, (int)lda, &beta, C, (int)ldc);
+  if (st != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSgemm failed (%d) M=%d N=%d K=%d", (int)st, M, N, K);
+  g_launch_count++;
+  return T2_OK;
+}
+
 namespace {
 
 constexpr int kSplit = 8;        // reduction splits of the skinny GEMMs (partials summed by the consumer)
@@ -57,10 +81,15 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs a) {
   for (int i = threadIdx.x; i < a.nvec; i += 256) s_vec[i] = a.vec[(long)b * a.ldvec + i];
   __syncthreads();
   float g_h = 0.f;
-  if (a.src0)
+  if (a.src0) {
+#pragma unroll
     for (int s = 0; s < kSplit; ++s) g_h += a.src0[((long)s * 64 + b) * a.ld0 + a.off0 + unit];
-  if (a.src1)
+  }
+  if (a.src1) {
+#pragma unroll
     for (int s = 0; s < kSplit; ++s) g_h += a.src1[((long)s * 64 + b) * a.ld1 + a.off1 + unit];
+  }
+#pragma unroll 8
   for (int o = 0; o < a.nvec; ++o) g_h = fmaf(s_vec[o], __ldg(a.Wv + (long)o * a.ldwv + unit), g_h);
   if (a.dropout) {
     const long idx = (long)b * 1024 + unit;
@@ -203,46 +232,63 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     s_pad0[15 + j] = t > 0 ? a.align[((long)b * T + t - 1) * Te + j] : 0.f;
     s_pad1[15 + j] = a.awc[((long)b * T + t) * Te + j];
     s_aw[j] = a.align[((long)b * T + t) * Te + j];
+    // carries into aw_t: location conv of step t+1 (channel 0) and the cumulative weights (channel 1 + running sum)
+    float g = 0.f, cv = 0.f;
+    if (a.carry) {
+      const float* g0 = a.gcat + (((long)rd * 2 + 0) * B + b) * 2 * Te;
+      const float* g1 = a.gcat + (((long)rd * 2 + 1) * B + b) * 2 * Te;
+      g = g0[j] + g1[j];
+      cv = a.cacc[((long)rd * B + b) * Te + j] + g0[Te + j] + g1[Te + j];
+    }
+    if (h == 0) a.cacc[((long)wr * B + b) * Te + j] = cv;
+    g += cv;
+    if (a.d_align) g += a.d_align[((long)b * T + t) * Te + j];
+    s_ge[j] = g;
   }
   // (1) total gradient wrt ctx_t: carry from step t+1's attention LSTM input, decoder LSTM input, projection
   for (int c = tid; c < 512; c += 256) {
     float g = 0.f;
-    if (a.carry)
+    if (a.carry) {
+#pragma unroll
       for (int s = 0; s < kSplit; ++s) g += a.PE[((long)s * 64 + b) * kPEld + 256 + c];
+    }
+#pragma unroll
     for (int s = 0; s < kSplit; ++s) g += a.PB[((long)s * 64 + b) * kPBld + 1024 + c];
+#pragma unroll 9
     for (int o = 0; o < 81; ++o) g = fmaf(s_dy[o], __ldg(a.wpg + (long)o * 1536 + 1024 + c), g);
     s_ctx[c] = g;
     if (h == 0) a.dctx[((long)t * B + b) * 512 + c] = g;
   }
   if (h == 0 && a.carry) {   // gradient wrt the prenet output of step t+1 (first 256 columns of KE's result)
     float g = 0.f;
+#pragma unroll
     for (int s = 0; s < kSplit; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
     a.dx2[((long)(t + 1) * B + b) * 256 + tid] = g;
   }
   __syncthreads();
-  // (2) g_aw[j] = memory[j] . g_ctx + carries (location conv of step t+1, cumulative weights)   model.py:83-84, 365
-  for (int j = warp; j < Te; j += 8) {
-    const float4* mr = reinterpret_cast<const float4*>(a.memory + ((long)b * Te + j) * 512);
-    float acc = 0.f;
+  // (2) g_aw[j] += memory[j] . g_ctx   (4 rows per warp iteration: 16 independent 16-byte loads in flight)  model.py:83-84
+  {
+    float4 gc[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 m = __ldg(mr + i * 32 + lane);
-      const float4 g = *reinterpret_cast<const float4*>(s_ctx + (i * 32 + lane) * 4);
-      acc += m.x * g.x + m.y * g.y + m.z * g.z + m.w * g.w;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float cv = 0.f;
-      if (a.carry) {
-        const float* g0 = a.gcat + (((long)rd * 2 + 0) * B + b) * 2 * Te;
-        const float* g1 = a.gcat + (((long)rd * 2 + 1) * B + b) * 2 * Te;
-        acc += g0[j] + g1[j];
-        cv = a.cacc[((long)rd * B + b) * Te + j] + g0[Te + j] + g1[Te + j];
+    for (int i = 0; i < 4; ++i) gc[i] = *reinterpret_cast<const float4*>(s_ctx + (i * 32 + lane) * 4);
+    for (int j0 = warp * 4; j0 < Te; j0 += 32) {
+      float acc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r] = 0.f;
+        const int j = j0 + r < Te ? j0 + r : Te - 1;
+        const float4* mr = reinterpret_cast<const float4*>(a.memory + ((long)b * Te + j) * 512);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 m = __ldg(mr + i * 32 + lane);
+          acc[r] += m.x * gc[i].x + m.y * gc[i].y + m.z * gc[i].z + m.w * gc[i].w;
+        }
       }
-      if (h == 0) a.cacc[((long)wr * B + b) * Te + j] = cv;
-      acc += cv;
-      if (a.d_align) acc += a.d_align[((long)b * T + t) * Te + j];
-      s_ge[j] = acc;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float v = warp_sum(acc[r]);
+        if (lane == 0 && j0 + r < Te) s_ge[j0 + r] += v;
+      }
     }
   }
   __syncthreads();
@@ -270,7 +316,9 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     const float vv = __ldg(a.v + ag);
     float gq = 0.f, dv = 0.f;
     for (int j0 = jg * 4; j0 < Te; j0 += 16) {
-      float pa[4] = {0.f, 0.f, 0.f, 0.f};
+      float pa[4] = {0.f, 0.f, 0.f, 0.f}, pmv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pmv[i] = j0 + i < Te ? __ldg(a.pm + ((long)b * Te + j0 + i) * 128 + ag) : 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const float* pad = (c == 0 ? s_pad0 : s_pad1) + j0;
@@ -286,7 +334,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
       for (int i = 0; i < 4; ++i) {
         const int j = j0 + i;
         if (j < Te) {
-          const float s = qv + pa[i] + __ldg(a.pm + ((long)b * Te + j) * 128 + ag);
+          const float s = qv + pa[i] + pmv[i];
           const float th = tanhf(s);
           const float ge = s_ge[j];
           const float g = ge * vv * (1.f - th * th);
@@ -423,30 +471,6 @@ __global__ void prenet_dz_kernel(const float* g, const float* __restrict__ act, 
   if (i < n) out[i] = act[i] > 0.f ? 2.f * g[i] : 0.f;
 }
 
-// ---- cuBLAS plumbing (plain time-batched GEMMs) ------------------------------------------------
-int blas_handle(T2Model* m, cudaStream_t s, cublasHandle_t* out) {
-  if (!m->blas) {
-    cublasHandle_t h;
-    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasCreate failed");
-    const char* e = getenv("T2_WGRAD_TF32");
-    cublasSetMathMode(h, (e && atoi(e)) ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH);
-    m->blas = h;
-  }
-  *out = (cublasHandle_t)m->blas;
-  if (cublasSetStream(*out, s) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSetStream failed");
-  return T2_OK;
-}
-// row-major C (M x N) = op(A) . op(B) + beta C;  ta: A is stored (K x M);  tb: B is stored (N x K)
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
-            float* C, long ldc, float beta) {
-  const float alpha = 1.f;
-  cublasStatus_t st = cublasSgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B,
-                                  (int)ldb, A, (int)lda, &beta, C, (int)ldc);
-  if (st != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSgemm failed (%d) M=%d N=%d K=%d", (int)st, M, N, K);
-  g_launch_count++;
-  return T2_OK;
-}
-
 struct BwdWs {
   float *dga, *dgd, *q, *dq, *awc, *pm, *dpm, *dctx, *dy, *gs, *cols, *pb, *pe, *gdc, *gac, *cacc, *gcat, *dv, *ones, *weff,
       *dweff, *tmp;
@@ -520,8 +544,25 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
   T2_TRY(gemm_rm(bl, false, true, (int)TB, kAtt, kARnn, st.ha + (size_t)B * kARnn, kARnn, m->w[W_ATT_QUERY], kARnn, w.q, kAtt, 0.f));
   T2_CUDA(cudaFuncSetAttribute(att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+  // T2_BWD_PROFILE=1: CUDA-event time per kernel class over the first 64 steps (stderr), for tuning
+  const bool prof = getenv("T2_BWD_PROFILE") != nullptr;
+  constexpr int kProfSteps = 64;
+  static cudaEvent_t pev[kProfSteps][6];
+  static bool pev_init = false;
+  if (prof && !pev_init) {
+    for (int i = 0; i < kProfSteps; ++i)
+      for (int j = 0; j < 6; ++j) cudaEventCreate(&pev[i][j]);
+    pev_init = true;
+  }
+  cudaEvent_t ph[4];
+  if (prof) { for (int i = 0; i < 4; ++i) cudaEventCreate(&ph[i]); cudaEventRecord(ph[0], s); }
+#define T2_TICK(i)                                                    \
+  do {                                                                \
+    if (prof && T - 1 - t < kProfSteps) cudaEventRecord(pev[T - 1 - t][i], s); \
+  } while (0)
   // ---- phase 1: reverse-time recurrence ---------------------------------------------------------------
   for (int t = T - 1; t >= 0; --t) {
+    T2_TICK(0);
     const int carry = t < T - 1;
     {  // KA
       LstmBwdArgs k;
@@ -535,6 +576,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
+    T2_TICK(1);
     {  // KB
       SkinnyArgs k;
       k.A = w.dgd + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
@@ -544,6 +586,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       skinny_nn_kernel<<<dim3(kPBld / 128, kSplit), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
+    T2_TICK(2);
     {  // KC
       AttBwdArgs k;
       memset(&k, 0, sizeof(k));
@@ -555,6 +598,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       att_bwd_kernel<<<dim3(2, B), 256, smem, s>>>(k);
       T2_LAUNCH_CHECK();
     }
+    T2_TICK(3);
     {  // KD
       LstmBwdArgs k;
       memset(&k, 0, sizeof(k));
@@ -568,6 +612,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
+    T2_TICK(4);
     {  // KE
       SkinnyArgs k;
       k.A = w.dga + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
@@ -577,7 +622,9 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       skinny_nn_kernel<<<dim3(kPEld / 128, kSplit), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
+    T2_TICK(5);
   }
+  if (prof) cudaEventRecord(ph[1], s);
   reduce_pe_x2_kernel<<<B, 256, 0, s>>>(w.pe, a->d_prenet, B);
   T2_LAUNCH_CHECK();
 
@@ -653,6 +700,21 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
                                                    a->align, Te, (long long)T * Te, &beta, a->d_memory, kEnc, (long long)Te * kEnc, B);
     if (stt != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSgemmStridedBatched failed (%d)", (int)stt);
     g_launch_count++;
+  }
+  if (prof) {
+    cudaEventRecord(ph[2], s);
+    cudaStreamSynchronize(s);
+    float acc[5] = {0, 0, 0, 0, 0};
+    const int n = T < kProfSteps ? T : kProfSteps;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < 5; ++j) { float ms = 0; cudaEventElapsedTime(&ms, pev[i][j], pev[i][j + 1]); acc[j] += ms; }
+    float m01 = 0, m12 = 0;
+    cudaEventElapsedTime(&m01, ph[0], ph[1]);
+    cudaEventElapsedTime(&m12, ph[1], ph[2]);
+    fprintf(stderr, "[t2b200] decoder backward: loop %.2f ms (%d steps), batched gradients %.2f ms; per step us: lstm_dec %.1f "
+            "gemm_dec %.1f attention %.1f lstm_att %.1f gemm_att %.1f\n", m01, T, m12, acc[0] / n * 1e3f, acc[1] / n * 1e3f,
+            acc[2] / n * 1e3f, acc[3] / n * 1e3f, acc[4] / n * 1e3f);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ph[i]);
   }
   return T2_OK;
 }

@@ -4,6 +4,7 @@
 
 #include "conv_tc.h"
 #include "gemm_f32.cuh"
+#include "train_layers.h"
 #include "model.h"
 
 namespace t2 {
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256, 1)
 enc_lstm_persistent_kernel(const float* __restrict__ gin, const float* __restrict__ whh_f,
                            const float* __restrict__ whh_r, float* __restrict__ hbuf,   // (2 buffers, 2 dirs, B, 256)
                            float* __restrict__ memory, const int32_t* __restrict__ lengths, int B, int T,
-                           EncLstmCtrl* ctrl) {
+                           EncLstmCtrl* ctrl, float* __restrict__ st_gates, float* __restrict__ st_c) {
   extern __shared__ float sm[];
   float* ws = sm;                        // [64 k4][16 rows][4]   (row = gate*4 + unit_local)
   float* hs = sm + kEncH * 16;           // [64 k4][64 batch][4]
@@ -243,7 +244,12 @@ enc_lstm_persistent_kernel(const float* __restrict__ gin, const float* __restric
         const float go = 1.f / (1.f + expf(-(acc[3] + gi4[3])));
         c = gf * c + gi * gg;
         hn = go * tanhf(c);
+        if (st_gates) {   // training stash: gate activations in the layout of gin
+          float* sg = st_gates + ((long)b * T + t) * (8 * kEncH) + dir * 4 * kEncH + unit;
+          sg[0] = gi; sg[kEncH] = gf; sg[2 * kEncH] = gg; sg[3 * kEncH] = go;
+        }
       }
+      if (st_c) st_c[((long)b * T + t) * kEnc + dir * kEncH + unit] = c;
       hprev = hn;
       hout[(long)b * kEncH + unit] = hn;
       memory[((long)b * T + t) * kEnc + dir * kEncH + unit] = valid ? hn : 0.f;
@@ -329,9 +335,18 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
   p = (char*)align256((size_t)p);
   __half* pl0 = (__half*)p; p += align256(tc_planes_bytes(B, T, kEnc));
   __half* pl1 = (__half*)p; p += align256(tc_planes_bytes(B, T, kEnc));
-  const bool tc = use_tc() && !a->training;
+  const bool tc = use_tc() && !a->training && !a->stash;
+  float* st_gates = nullptr; float* st_c = nullptr;
 
-  if (tc) {
+  if (a->stash) {
+    // autograd path: fp32 conv stack with the activations kept for the backward pass (train_layers.cu)
+    const float* xl = nullptr;
+    T2_TRY(encoder_convs_train(m, a, s, &xl, &st_gates, &st_c));
+    GemmArgs g;
+    g.seg[0] = {xl, kEnc, m->enc_lstm_wih, kEnc, kEnc};
+    g.M = B * T; g.N = 8 * kEncH; g.C = gin; g.ldc = 8 * kEncH; g.bias = m->enc_lstm_b;
+    T2_TRY(gemm_f32(g, s));
+  } else if (tc) {
     // tensor-core path: planes -> 3 x (conv k5 + folded BN + ReLU) -> LSTM input projection (fp32 rows)
     if (a->embedded) T2_TRY(tc_rows_to_planes(a->embedded, (long)T * kEnc, kEnc, kEnc, nullptr, B, T, pl0, s));
     else T2_TRY(tc_embed_to_planes(a->text, m->w[W_EMB], m->cfg.n_symbols, B, T, pl0, s));
@@ -383,11 +398,14 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
     T2_CUDA(cudaFuncSetAttribute(enc_lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     const float* whf = m->w[W_ENC_LSTM + 1]; const float* whr = m->w[W_ENC_LSTM + 5];
     const int32_t* lens = a->lengths; float* mem = a->memory; int Bv = B, Tv = T;
-    void* args[] = {(void*)&gin, (void*)&whf, (void*)&whr, (void*)&hb, (void*)&mem, (void*)&lens, (void*)&Bv, (void*)&Tv, (void*)&lctrl};
+    void* args[] = {(void*)&gin, (void*)&whf, (void*)&whr, (void*)&hb, (void*)&mem, (void*)&lens, (void*)&Bv, (void*)&Tv, (void*)&lctrl,
+                    (void*)&st_gates, (void*)&st_c};
     T2_CUDA(cudaLaunchCooperativeKernel((void*)enc_lstm_persistent_kernel, dim3(128), dim3(256), args, psm, s));
     g_launch_count++;
+    if (a->stash) T2_TRY(encoder_stash_output(a, s));
     return T2_OK;
   }
+  if (a->stash) return fail(T2_ERR_UNSUPPORTED, "encoder: the training stash needs B <= 64 (persistent BiLSTM kernel)");
   const size_t smem = (64 * kEncH + 64 * (kEncH + 1)) * sizeof(float);
   T2_CUDA(cudaFuncSetAttribute(enc_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* hin = hbuf0; float* hout = hbuf1;

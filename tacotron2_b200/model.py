@@ -92,6 +92,77 @@ def _require_no_grad(module, what):
             "engine); wrap the call in torch.no_grad()" % what)
 
 
+def _wants_grad(module, *tensors):
+    return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
+                                        any(p_.requires_grad for p_ in module.parameters()))
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Encoder.forward (model.py:173-190) [+ the embedding lookup of model.py:503 when `text` is given] as one autograd
+    node: forward = fp32 conv stack + persistent BiLSTM with a stash, backward = t2_encoder_backward."""
+
+    @staticmethod
+    def forward(ctx, owner, prefix_params, text, embedded, lengths, training, *params):
+        eng = owner._t2_engine()
+        keep = current_masks()["enc"]
+        seed = next_seed()
+        src = text if text is not None else embedded
+        B, T = int(src.shape[0]), int(src.shape[1])
+        stash = eng.stash_buffer("encoder", B, T)
+        emb32 = None
+        if embedded is not None:
+            emb32 = embedded.detach().to(dtype=torch.float32).contiguous()
+        memory = eng.encoder(text=text, embedded=emb32, lengths=lengths, training=training, keep=keep, stash=stash, seed=seed)
+        ctx.saved = dict(eng=eng, text=text, embedded=emb32, lengths=lengths, training=training, keep=keep, seed=seed,
+                         stash=stash, names=prefix_params, params=params,
+                         emb_dtype=embedded.dtype if embedded is not None else None)
+        return memory
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_memory):
+        sv = ctx.saved
+        f32 = dict(device=d_memory.device, dtype=torch.float32)
+        grads = {n: torch.empty(p_.shape, **f32) for n, p_ in zip(sv["names"], sv["params"])}
+        d_emb = sv["eng"].encoder_backward(sv["text"], sv["embedded"], sv["lengths"], sv["training"], sv["keep"], sv["seed"],
+                                           sv["stash"], d_memory, sv["embedded"] is not None, grads)
+        ctx.saved = None
+        if d_emb is not None:
+            d_emb = d_emb.to(sv["emb_dtype"])
+        return (None, None, None, d_emb, None, None) + tuple(grads[n].to(p_.dtype) for n, p_ in zip(sv["names"], sv["params"]))
+
+
+class _PostnetFn(torch.autograd.Function):
+    """Postnet.forward (model.py:141-146) [+ the residual of model.py:511 when add_residual] as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, owner, names, mel_btc, add_residual, training, wgrad_lengths, *params):
+        eng = owner._t2_engine()
+        keep = current_masks()["post"]
+        seed = next_seed()
+        x = mel_btc.detach()
+        if x.dtype != torch.float32 or x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+            x = x.float().contiguous()
+        B, T = int(x.shape[0]), int(x.shape[1])
+        stash = eng.stash_buffer("postnet", B, T)
+        out = eng.postnet(x, None, add_residual, training, keep, stash=stash, seed=seed)
+        ctx.saved = dict(eng=eng, B=B, T=T, add_residual=add_residual, training=training, keep=keep, seed=seed, stash=stash,
+                         names=names, params=params, in_dtype=mel_btc.dtype, wgrad_lengths=wgrad_lengths)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out):
+        sv = ctx.saved
+        f32 = dict(device=d_out.device, dtype=torch.float32)
+        grads = {n: torch.empty(p_.shape, **f32) for n, p_ in zip(sv["names"], sv["params"])}
+        d_mel = sv["eng"].postnet_backward(sv["B"], sv["T"], sv["training"], sv["add_residual"], sv["keep"], sv["seed"],
+                                           sv["stash"], d_out, grads, sv["wgrad_lengths"])
+        ctx.saved = None
+        return (None, None, d_mel.to(sv["in_dtype"]), None, None, None) + tuple(grads[n].to(p_.dtype) for n, p_ in
+                                                                          zip(sv["names"], sv["params"]))
+
+
 class Prenet(nn.Module, _EngineOwner):
     """model.py:89-100.  Dropout(0.5) is always on, as in the reference (model.py:99)."""
     _t2_prefix = "decoder.prenet."
@@ -142,12 +213,15 @@ class Postnet(nn.Module, _EngineOwner):
                 nn.BatchNorm1d(hparams.n_mel_channels)))
 
     def _run(self, x, lengths, add_residual):
-        _require_no_grad(self, "Postnet.forward")
-        eng = self._t2_engine()
         xt = x.transpose(1, 2)                       # (B, T, 80): the decoder's native storage
+        if lengths is None and _wants_grad(self, x):
+            named = [("postnet." + k, p_) for k, p_ in self.named_parameters()]
+            return _PostnetFn.apply(self, [n for n, _ in named], xt, add_residual, self.training, None,
+                                    *[p_ for _, p_ in named]).to(x.dtype)
+        eng = self._t2_engine()
         if xt.dtype != torch.float32 or xt.stride(2) != 1 or xt.stride(1) != xt.shape[2]:
             xt = xt.float().contiguous()
-        return eng.postnet(xt, lengths, add_residual, self.training, current_masks()["post"]).to(x.dtype)
+        return eng.postnet(xt.detach(), lengths, add_residual, self.training, current_masks()["post"]).to(x.dtype)
 
     def forward(self, x):
         """x (B, n_mel, T) -> postnet(x) (B, n_mel, T); the caller adds the residual (model.py:511)."""
@@ -174,10 +248,13 @@ class Encoder(nn.Module, _EngineOwner):
                             batch_first=True, bidirectional=True)
 
     def _run(self, x, lengths):
-        _require_no_grad(self, "Encoder.forward")
-        eng = self._t2_engine()
         emb = x.transpose(1, 2)                      # (B, T, 512) -- contiguous when x came from the embedding
-        out = eng.encoder(embedded=emb, lengths=lengths, training=self.training, keep=current_masks()["enc"])
+        if _wants_grad(self, x):
+            named = [("encoder." + k, p_) for k, p_ in self.named_parameters()]
+            return _EncoderFn.apply(self, [n for n, _ in named], None, emb, lengths, self.training,
+                                    *[p_ for _, p_ in named]).to(x.dtype)
+        eng = self._t2_engine()
+        out = eng.encoder(embedded=emb.detach(), lengths=lengths, training=self.training, keep=current_masks()["enc"])
         return out.to(x.dtype)
 
     def forward(self, x, input_lengths):
@@ -371,17 +448,30 @@ class Tacotron2(nn.Module, _EngineOwner):
 
     def forward(self, inputs):
         """model.py:499-515."""
-        _require_no_grad(self, "Tacotron2.forward")
         text_inputs, text_lengths, mels, max_len, output_lengths = inputs
         text_lengths, output_lengths = text_lengths.data, output_lengths.data
         eng = self._t2_engine()
         masks = current_masks()
-        memory = eng.encoder(text=text_inputs, lengths=text_lengths, training=self.training, keep=masks["enc"])
+        grad = _wants_grad(self)
+        if grad:   # embedding lookup + encoder as one node (the embedding gradient comes out of t2_encoder_backward)
+            named = [("embedding.weight", self.embedding.weight)] + [("encoder." + k, p_) for k, p_ in self.encoder.named_parameters()]
+            memory = _EncoderFn.apply(self, [n for n, _ in named], text_inputs, None, text_lengths, self.training,
+                                      *[p_ for _, p_ in named])
+        else:
+            memory = eng.encoder(text=text_inputs, lengths=text_lengths, training=self.training, keep=masks["enc"])
         mel_outputs, gate_outputs, alignments = self.decoder(memory, mels, memory_lengths=text_lengths)
         mel_btc = mel_outputs.transpose(1, 2)
-        if mel_btc.dtype != torch.float32 or not mel_btc.is_contiguous():
-            mel_btc = mel_btc.float().contiguous()
-        mel_outputs_postnet = eng.postnet(mel_btc, None, True, self.training, masks["post"]).to(mel_outputs.dtype)
+        if grad:
+            named = [("postnet." + k, p_) for k, p_ in self.postnet.named_parameters()]
+            # parse_output below zeroes the padded frames of mel_outputs in place (model.py:492); in the reference that
+            # tensor is what the first postnet conv saved for its weight gradient -> reproduce (wgrad_lengths)
+            wl = output_lengths if self.mask_padding else None
+            mel_outputs_postnet = _PostnetFn.apply(self, [n for n, _ in named], mel_btc, True, self.training, wl,
+                                                   *[p_ for _, p_ in named]).to(mel_outputs.dtype)
+        else:
+            if mel_btc.dtype != torch.float32 or not mel_btc.is_contiguous():
+                mel_btc = mel_btc.float().contiguous()
+            mel_outputs_postnet = eng.postnet(mel_btc, None, True, self.training, masks["post"]).to(mel_outputs.dtype)
         if self.training:
             for mod in self.modules():
                 if isinstance(mod, nn.BatchNorm1d) and mod.num_batches_tracked is not None:

@@ -94,7 +94,12 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     src = tmp_path / "layout.c"
     fields = {
         "T2Config": ["n_mel_channels", "postnet_n_convolutions", "p_attention_dropout", "bn_eps"],
-        "T2EncoderArgs": ["text", "embedded", "lengths", "B", "T", "training", "keep", "seed", "memory", "ws", "ws_bytes"],
+        "T2EncoderArgs": ["text", "embedded", "lengths", "B", "T", "training", "keep", "seed", "memory", "ws", "ws_bytes",
+                          "stash", "stash_bytes"],
+        "T2EncoderBwdArgs": ["text", "embedded", "lengths", "B", "T", "training", "keep", "seed", "stash", "stash_bytes",
+                             "d_memory", "d_embedded", "grads", "n_grads", "ws", "ws_bytes"],
+        "T2PostnetBwdArgs": ["B", "T", "training", "add_residual", "keep", "seed", "wgrad_lengths", "stash", "stash_bytes",
+                             "d_mel_post", "d_mel", "grads", "n_grads", "ws", "ws_bytes"],
         "T2DecoderArgs": ["mode", "impl", "training", "memory", "memory_lengths", "B", "T_enc", "n_steps_cap",
                           "teacher_prenet", "prenet_keep", "att_keep", "dec_keep", "seed", "gate_threshold",
                           "score_mask_value", "mel", "gate", "align", "mel_lengths", "n_steps", "ws", "ws_bytes",
@@ -104,7 +109,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
                              "d_align", "d_memory", "d_prenet", "grads", "n_grads", "ws", "ws_bytes"],
         "T2PrenetBwdArgs": ["frames", "M", "keep", "seed", "d_out", "grads", "n_grads", "ws", "ws_bytes"],
         "T2PostnetArgs": ["mel", "mel_batch_stride", "lengths", "B", "T", "training", "keep", "seed",
-                          "add_residual", "mel_post", "ws", "ws_bytes"],
+                          "add_residual", "mel_post", "ws", "ws_bytes", "stash", "stash_bytes"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "t2b200.h"', 'int main(void){']
     for s, fs in fields.items():

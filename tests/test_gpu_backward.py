@@ -9,6 +9,7 @@ import torch
 import tacotron2_b200 as t2
 from oracle import tacotron2_oracle as O
 from tests.common import keep_mask, rel_err, synth_state_dict
+from tests.test_oracle_golden import GRADS, check_grads_vs_fixture, grad_inputs, load, oracle_train_step
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -73,4 +74,81 @@ def test_decoder_backward_vs_oracle_autograd(B, Te, T, training, use_align):
         errs[k] = rel_err(p.grad, ref_g["decoder." + k])
     bad = {k: v for k, v in errs.items() if not v < TOL}
     print("decoder backward B=%d Te=%d T=%d: worst %.2e" % (B, Te, T, max(errs.values())))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", GRADS)
+def test_full_train_step_matches_reference_gradient_golden(name):
+    """Tacotron2.forward + Tacotron2Loss + backward through the CUDA path vs (a) the gradients the reference's own
+    autograd produced (tests/golden/grad_*.npz) and (b) the oracle's autograd, every parameter, full tensors."""
+    g = load(name)
+    training = bool(int(g["training"]))
+    sd, text, tl, ol, mels, gt, m = grad_inputs(g)
+    ref_loss, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, training)
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda().train(training)
+    post_keep = [m["qk4"][i] for i in range(4)] + [m["qk1"]]
+    with t2.dropout_masks(prenet=m["pk"], att=m["ak"], dec=m["dk"], enc=m["ek"], post=post_keep):
+        out = model((text.cuda(), tl.cuda(), mels.cuda(), int(tl.max()), ol.cuda()))
+        loss = t2.Tacotron2Loss()(out, (mels.cuda(), gt.cuda()))
+        loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert rel_err(out[0], torch.from_numpy(g["mel"])) < TOL and rel_err(out[1], torch.from_numpy(g["mel_post"])) < TOL
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert all(v is not None for v in grads.values())
+    check_grads_vs_fixture(grads, g, TOL)
+    errs = {}
+    for k, v in grads.items():
+        if float(ref_g[k].abs().max()) < 1e-5:
+            continue
+        errs[k] = rel_err(v, ref_g[k])
+    print("train step %s: loss %.6f (ref %.6f), worst gradient error %.2e" % (name, float(loss), float(ref_loss), max(errs.values())))
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("B,T", [(3, 21), (5, 64)])
+def test_postnet_and_encoder_modules_backward_vs_oracle(B, T):
+    """The Encoder and Postnet nn.Modules on their own under autograd (training mode, injected masks)."""
+    sd = synth_state_dict(seed=33, scale=2.0)
+    g = torch.Generator().manual_seed(B * 100 + T)
+    x = torch.randn(B, 80, T, generator=g)
+    emb = torch.randn(B, 512, T, generator=g)
+    lens = torch.sort(torch.randint(max(1, T // 2), T + 1, (B,), generator=g), descending=True)[0]
+    lens[0] = T
+    post_keep = [keep_mask((B, 512, T), 0.5, 7 + i) for i in range(4)] + [keep_mask((B, 80, T), 0.5, 11)]
+    ek = keep_mask((3, B, 512, T), 0.5, 12)
+    d_post = torch.randn(B, 80, T, generator=g)
+    d_mem = torch.randn(B, T, 512, generator=g)
+    # oracle
+    names = [k for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k and not k.startswith("decoder.")]
+    sdg = dict(sd)
+    for k in names:
+        sdg[k] = sd[k].clone().requires_grad_(True)
+    xo, eo = x.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    (O.postnet(sdg, xo, True, post_keep) * d_post).sum().backward()
+    (O.encoder(sdg, eo, lens, True, ek) * d_mem).sum().backward()
+    # engine
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    xe, ee = x.cuda().requires_grad_(True), emb.cuda().requires_grad_(True)
+    with t2.dropout_masks(enc=ek, post=post_keep):
+        (model.postnet(xe) * d_post.cuda()).sum().backward()
+        (model.encoder(ee, lens.cuda()) * d_mem.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    errs = {"d_x": rel_err(xe.grad, xo.grad), "d_emb": rel_err(ee.grad, eo.grad)}
+    for k, p in model.named_parameters():
+        if k.startswith("postnet.") or k.startswith("encoder."):
+            assert p.grad is not None, k
+            if k.endswith("conv.bias"):
+                # a bias in front of a training-mode BatchNorm has an exactly-zero gradient; both sides hold rounding noise
+                scale = float(sdg[k.replace("0.conv.bias", "1.bias")].grad.abs().max())
+                assert float(sdg[k].grad.abs().max()) < 1e-3 * scale and float(p.grad.abs().max()) < 1e-3 * scale, k
+                continue
+            errs[k] = rel_err(p.grad, sdg[k].grad)
+    print("encoder/postnet backward B=%d T=%d: worst %.2e" % (B, T, max(errs.values())))
+    bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad

@@ -151,7 +151,75 @@ def forward_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
          bn0_running_var=sd_after["encoder.convolutions.0.1.running_var"])
 
 
+def grad_sample_index(name, numel, n=96):
+    """Deterministic flat indices at which the gradient of parameter `name` is stored in the fixture."""
+    h = 0
+    for ch in name:
+        h = (h * 131 + ord(ch)) % 2147483647
+    g = torch.Generator().manual_seed(h)
+    return torch.randint(0, numel, (min(n, numel),), generator=g)
+
+
+def gate_targets(ol, T_mel):
+    """data_utils.py:105-107: gate_padded[i, len_i - 1:] = 1."""
+    gt = torch.zeros(len(ol), T_mel)
+    for i, n in enumerate(ol.tolist()):
+        gt[i, n - 1:] = 1.0
+    return gt
+
+
+def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
+    """Full training step of the REFERENCE (forward + Tacotron2Loss + backward, autograd) with injected dropout
+    masks; the fixture keeps the loss and, per parameter, sum / abs-sum / max of the gradient plus 96 sampled entries."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_loss_function", "/root/reference/loss_function.py")
+    lf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lf)
+    sd = synth_state_dict(wseed, scale=wscale)
+    g = torch.Generator().manual_seed(seed)
+    text = rand_text(B, T_text, seed + 1)
+    tl = torch.sort(torch.randint(T_text // 3, T_text + 1, (B,), generator=g), descending=True)[0]
+    tl[0] = T_text
+    ol = torch.randint(T_mel // 3, T_mel + 1, (B,), generator=g); ol[1] = T_mel
+    mels = torch.randn(B, 80, T_mel, generator=g)
+    for i, n in enumerate(ol.tolist()):
+        mels[i, :, n:] = 0.0                                    # TextMelCollate zero-pads (data_utils.py:97-104)
+    pk = keep_mask((T_mel + 1, 2, B, 256), 0.5, seed + 2)
+    ak = keep_mask((T_mel, B, 1024), 0.1, seed + 3)
+    dk = keep_mask((T_mel, B, 1024), 0.1, seed + 4)
+    ek = keep_mask((3, B, 512, T_text), 0.5, seed + 5)
+    qk4 = keep_mask((4, B, 512, T_mel), 0.5, seed + 6)
+    qk1 = keep_mask((B, 80, T_mel), 0.5, seed + 7)
+    model = build(sd, training)
+    if training:
+        masks = [ek[i].bool() for i in range(3)] + [pk[:, 0].bool(), pk[:, 1].bool()]
+        for t in range(T_mel):
+            masks += [ak[t].bool(), dk[t].bool()]
+        masks += [qk4[i].bool() for i in range(4)] + [qk1.bool()]
+    else:
+        masks = [pk[:, 0].bool(), pk[:, 1].bool()]
+    gt = gate_targets(ol, T_mel)
+    with injected_dropout(ref, MaskInjector(masks)) as inj:
+        out = model((text, tl, mels, int(tl.max()), ol))
+        assert inj.calls == len(masks)
+    loss = lf.Tacotron2Loss()(out, (mels, gt))
+    loss.backward()
+    arrays = dict(training=int(training), B=B, T_text=T_text, T_mel=T_mel, wseed=wseed, seed=seed, wscale=wscale,
+                  wsum=weights_checksum(sd), text_lengths=tl, output_lengths=ol, mels_in=mels, gate_target=gt,
+                  loss=loss.detach(), mel=out[0].detach(), mel_post=out[1].detach())
+    for k, p_ in model.named_parameters():
+        gr = p_.grad.detach().double().reshape(-1)
+        idx = grad_sample_index(k, gr.numel())
+        arrays["g/" + k] = torch.cat((torch.stack((gr.sum(), gr.abs().sum(), gr.abs().max())), gr[idx]))
+    print(name, "loss", float(loss))
+    save(name, **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":
+        grad_case("grad_train_b4", True, 4, 24, 12, 1234, 60)
+        grad_case("grad_eval_b3", False, 3, 17, 9, 77, 70)
+        sys.exit(0)
     infer_case("infer_b1_t50", 1, 50, 40, 0.95, 1234, 11, 12)
     infer_case("infer_b4_t24", 4, 24, 32, 0.93, 1234, 21, 22)
     infer_case("infer_b3_t37", 3, 37, 16, 0.90, 77, 31, 32, wscale=1.0)
