@@ -46,7 +46,9 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float
 
 namespace {
 
-constexpr int kSplit = 8;        // reduction splits of the skinny GEMMs (partials summed by the consumer)
+constexpr int kSplitB = 7;       // reduction splits of the skinny GEMMs (partials summed by the consumer):
+constexpr int kSplitE = 10;      // 20 x 7 = 14 x 10 = 140 CTAs = one wave of one CTA per SM
+constexpr int kSplitMax = 10;
 constexpr int kPBld = 1536 + 1024;   // [g_ah (1024) | g_ctx (512) | g_dh' (1024)]
 constexpr int kPEld = 768 + 1024;    // [g_x2 (256) | g_ctx' (512) | g_ah' (1024)]
 constexpr int kTaps = 2 * kLocK;     // 62 taps of the fused location filter
@@ -63,8 +65,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 struct LstmBwdArgs {
   // g_h = sum over sources of sum_s src[(s * 64 + b) * ld + off + unit]  +  sum_o vec[b][o] * Wv[o][unit]
-  const float* src0; int ld0, off0;
-  const float* src1; int ld1, off1;
+  const float* src0; int ld0, off0, ns0;
+  const float* src1; int ld1, off1, ns1;
+  const float* add; int ldadd;             // (B, >= 1024) direct term or null
   const float* vec; int nvec, ldvec;       // (B, nvec) rows, row stride ldvec
   const float* Wv; int ldwv;               // (nvec, >= 1024)
   const uint8_t* keep;                     // (B, 1024) of this step or null
@@ -80,17 +83,24 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs a) {
   const int b = blockIdx.y, unit = blockIdx.x * 256 + threadIdx.x;
   for (int i = threadIdx.x; i < a.nvec; i += 256) s_vec[i] = a.vec[(long)b * a.ldvec + i];
   __syncthreads();
-  float g_h = 0.f;
+  float g_h = a.add ? a.add[(long)b * a.ldadd + unit] : 0.f;
   if (a.src0) {
-#pragma unroll
-    for (int s = 0; s < kSplit; ++s) g_h += a.src0[((long)s * 64 + b) * a.ld0 + a.off0 + unit];
+#pragma unroll 5
+    for (int s = 0; s < a.ns0; ++s) g_h += a.src0[((long)s * 64 + b) * a.ld0 + a.off0 + unit];
   }
   if (a.src1) {
-#pragma unroll
-    for (int s = 0; s < kSplit; ++s) g_h += a.src1[((long)s * 64 + b) * a.ld1 + a.off1 + unit];
+#pragma unroll 5
+    for (int s = 0; s < a.ns1; ++s) g_h += a.src1[((long)s * 64 + b) * a.ld1 + a.off1 + unit];
   }
-#pragma unroll 8
-  for (int o = 0; o < a.nvec; ++o) g_h = fmaf(s_vec[o], __ldg(a.Wv + (long)o * a.ldwv + unit), g_h);
+  {
+    float p4[4] = {0.f, 0.f, 0.f, 0.f};     // nvec is a multiple of 4 (0 or 128)
+#pragma unroll 4
+    for (int o = 0; o < a.nvec; o += 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p4[i] = fmaf(s_vec[o + i], __ldg(a.Wv + (long)(o + i) * a.ldwv + unit), p4[i]);
+    }
+    g_h += (p4[0] + p4[1]) + (p4[2] + p4[3]);
+  }
   if (a.dropout) {
     const long idx = (long)b * 1024 + unit;
     const bool keep = a.keep ? a.keep[idx] != 0 : philox_keep(a.seed, a.site, (uint64_t)idx, a.p);
@@ -120,6 +130,7 @@ struct SkinnyArgs {
   const float* W0; int ldw0; int cols0;
   const float* W1; int ldw1; int cols1;
   float* P; int ldp;
+  int nsplit;                               // gridDim.y; the nred / 32 chunks are divided as evenly as possible
 };
 
 __global__ void __launch_bounds__(256) skinny_nn_kernel(const SkinnyArgs a) {
@@ -132,8 +143,9 @@ __global__ void __launch_bounds__(256) skinny_nn_kernel(const SkinnyArgs a) {
   const float* W; int ldw; int col_out;
   if (ct < tiles0) { W = a.W0 + ct * 128; ldw = a.ldw0; col_out = ct * 128; }
   else { W = a.W1 + (ct - tiles0) * 128; ldw = a.ldw1; col_out = ct * 128; }
-  const int per = a.nred / kSplit;
-  const int n_begin = blockIdx.y * per, n_end = n_begin + per;
+  const int nchunks = a.nred / BK;
+  const int n_begin = (int)((long)blockIdx.y * nchunks / a.nsplit) * BK;
+  const int n_end = (int)((long)(blockIdx.y + 1) * nchunks / a.nsplit) * BK;
   float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -197,7 +209,8 @@ struct AttBwdArgs {
   const float* align; const float* awc;   // (B,T,Te) forward weights / cumulative weights BEFORE step t
   const float* d_align;                   // (B,T,Te) or null
   const float* PE; const float* PB;       // partials of step t+1 (KE) and of this step (KB)
-  const float* dY; const float* wpg;      // (T,B,81), (81,1536)
+  const float* gproj;                     // (T,B,1536) = [d_mel_t ; d_gate_t] . W_PG, all steps (time batched)
+  const float* weffT;                     // (62, 128) transposed fused location filter
   float* dctx; float* dx2; float* dq;     // (T,B,512), (T,B,256), (T,B,128)
   float* gs;                              // (T,B,Te,128)
   float* gcat;                            // (2 pingpong, 2 halves, B, 2, Te)
@@ -224,7 +237,6 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   float* s_u = s_gs + (size_t)Te4 * 64;    // Te x 65
   const int rd = (t + 1) & 1, wr = t & 1;
 
-  if (tid < 81) s_dy[tid] = a.dY[((long)t * B + b) * 81 + tid];
   // previous / cumulative attention weights of this step (zero padded by 15 each side)   model.py:358-360
   for (int i = tid; i < TeP4; i += 256) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }
   __syncthreads();
@@ -247,22 +259,20 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   }
   // (1) total gradient wrt ctx_t: carry from step t+1's attention LSTM input, decoder LSTM input, projection
   for (int c = tid; c < 512; c += 256) {
-    float g = 0.f;
+    float g = a.gproj[((long)t * B + b) * 1536 + 1024 + c];
     if (a.carry) {
 #pragma unroll
-      for (int s = 0; s < kSplit; ++s) g += a.PE[((long)s * 64 + b) * kPEld + 256 + c];
+      for (int s = 0; s < kSplitE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + 256 + c];
     }
 #pragma unroll
-    for (int s = 0; s < kSplit; ++s) g += a.PB[((long)s * 64 + b) * kPBld + 1024 + c];
-#pragma unroll 9
-    for (int o = 0; o < 81; ++o) g = fmaf(s_dy[o], __ldg(a.wpg + (long)o * 1536 + 1024 + c), g);
+    for (int s = 0; s < kSplitB; ++s) g += a.PB[((long)s * 64 + b) * kPBld + 1024 + c];
     s_ctx[c] = g;
     if (h == 0) a.dctx[((long)t * B + b) * 512 + c] = g;
   }
   if (h == 0 && a.carry) {   // gradient wrt the prenet output of step t+1 (first 256 columns of KE's result)
     float g = 0.f;
 #pragma unroll
-    for (int s = 0; s < kSplit; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
+    for (int s = 0; s < kSplitE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
     a.dx2[((long)(t + 1) * B + b) * 256 + tid] = g;
   }
   __syncthreads();
@@ -271,10 +281,10 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     float4 gc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) gc[i] = *reinterpret_cast<const float4*>(s_ctx + (i * 32 + lane) * 4);
-    for (int j0 = warp * 4; j0 < Te; j0 += 32) {
-      float acc[4];
+    for (int j0 = warp * 8; j0 < Te; j0 += 64) {
+      float acc[8];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < 8; ++r) {
         acc[r] = 0.f;
         const int j = j0 + r < Te ? j0 + r : Te - 1;
         const float4* mr = reinterpret_cast<const float4*>(a.memory + ((long)b * Te + j) * 512);
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
         }
       }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < 8; ++r) {
         const float v = warp_sum(acc[r]);
         if (lane == 0 && j0 + r < Te) s_ge[j0 + r] += v;
       }
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     const int al = tid & 63, jg = tid >> 6, ag = h * 64 + al;
     float w[kTaps];
 #pragma unroll
-    for (int k = 0; k < kTaps; ++k) w[k] = __ldg(a.weff + (long)ag * kTaps + k);
+    for (int k = 0; k < kTaps; ++k) w[k] = __ldg(a.weffT + (long)k * kAtt + ag);
     const float qv = a.q[((long)t * B + b) * 128 + ag];
     const float vv = __ldg(a.v + ag);
     float gq = 0.f, dv = 0.f;
@@ -408,13 +418,15 @@ __global__ void awc_kernel(const float* __restrict__ align, float* __restrict__ 
     run += align[((long)b * T + t) * Te + j];
   }
 }
-__global__ void weff_kernel(const float* __restrict__ wld, const float* __restrict__ wloc, float* __restrict__ weff) {
+__global__ void weff_kernel(const float* __restrict__ wld, const float* __restrict__ wloc, float* __restrict__ weff,
+                            float* __restrict__ weffT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // Weff[a][c*31+k] = sum_f W_ld[a][f] W_loc[f][c][k]
   if (i >= kAtt * kTaps) return;
   const int a = i / kTaps, ck = i - a * kTaps;
   float s = 0.f;
   for (int f = 0; f < kLocF; ++f) s = fmaf(wld[a * kLocF + f], wloc[f * kTaps + ck], s);
   weff[i] = s;
+  weffT[(long)ck * kAtt + a] = s;
 }
 __global__ void dweff_split_kernel(const float* __restrict__ dweff, const float* __restrict__ wld, const float* __restrict__ wloc,
                                    float* __restrict__ d_wld, float* __restrict__ d_wloc) {
@@ -451,7 +463,7 @@ __global__ void reduce_pe_x2_kernel(const float* __restrict__ PE, float* __restr
   const int b = blockIdx.x, c = threadIdx.x;   // step 0: g_x2 = sum of the partials
   if (b >= B) return;
   float g = 0.f;
-  for (int s = 0; s < kSplit; ++s) g += PE[((long)s * 64 + b) * kPEld + c];
+  for (int s = 0; s < kSplitE; ++s) g += PE[((long)s * 64 + b) * kPEld + c];
   dx2[(long)b * 256 + c] = g;
 }
 __global__ void fill_kernel(float* p, float v, long n) {
@@ -473,7 +485,7 @@ __global__ void prenet_dz_kernel(const float* g, const float* __restrict__ act, 
 
 struct BwdWs {
   float *dga, *dgd, *q, *dq, *awc, *pm, *dpm, *dctx, *dy, *gs, *cols, *pb, *pe, *gdc, *gac, *cacc, *gcat, *dv, *ones, *weff,
-      *dweff, *tmp;
+      *dweff, *tmp, *gproj, *weffT;
 };
 size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   uintptr_t p = (uintptr_t)base;
@@ -486,7 +498,7 @@ size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   d.pm = take((size_t)B * Te * 128); d.dpm = take((size_t)B * Te * 128);
   d.dctx = take(TB * 512); d.dy = take(TB * 81);
   d.gs = take(TB * Te * 128); d.cols = take(TB * Te * kColsLd);
-  d.pb = take((size_t)kSplit * 64 * kPBld); d.pe = take((size_t)kSplit * 64 * kPEld);
+  d.pb = take((size_t)kSplitMax * 64 * kPBld); d.pe = take((size_t)kSplitMax * 64 * kPEld);
   d.gdc = take((size_t)64 * 1024); d.gac = take((size_t)64 * 1024);
   d.cacc = take((size_t)2 * B * Te); d.gcat = take((size_t)2 * 2 * B * 2 * Te);
   d.dv = take((size_t)B * 128);
@@ -494,6 +506,7 @@ size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   d.ones = take(n_ones);
   d.weff = take((size_t)kAtt * kTaps); d.dweff = take((size_t)kAtt * kColsLd);
   d.tmp = take(4096);
+  d.gproj = take(TB * 1536); d.weffT = take((size_t)kAtt * kTaps);
   if (w) *w = d;
   return (size_t)(p - (uintptr_t)base);
 }
@@ -533,7 +546,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     T2_LAUNCH_CHECK();
     awc_kernel<<<(B * Te + 127) / 128, 128, 0, s>>>(a->align, w.awc, B, T, Te);
     T2_LAUNCH_CHECK();
-    weff_kernel<<<(kAtt * kTaps + 255) / 256, 256, 0, s>>>(m->w[W_ATT_LOC_DENSE], m->w[W_ATT_LOC_CONV], w.weff);
+    weff_kernel<<<(kAtt * kTaps + 255) / 256, 256, 0, s>>>(m->w[W_ATT_LOC_DENSE], m->w[W_ATT_LOC_CONV], w.weff, w.weffT);
     T2_LAUNCH_CHECK();
     const size_t n_ones = TB > (size_t)B * Te ? TB : (size_t)B * Te;
     fill_kernel<<<(unsigned)((n_ones + 255) / 256), 256, 0, s>>>(w.ones, 1.f, (long)n_ones);
@@ -542,6 +555,8 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
   // processed_memory (model.py:288) and the processed queries of all steps (model.py:57)
   T2_TRY(gemm_rm(bl, false, true, B * Te, kAtt, kEnc, a->memory, kEnc, m->w[W_ATT_MEMORY], kEnc, w.pm, kAtt, 0.f));
   T2_TRY(gemm_rm(bl, false, true, (int)TB, kAtt, kARnn, st.ha + (size_t)B * kARnn, kARnn, m->w[W_ATT_QUERY], kARnn, w.q, kAtt, 0.f));
+  // projection / gate contribution to g_dh and g_ctx of every step: [d_mel_t ; d_gate_t] . [W_proj ; W_gate]  (model.py:373-378)
+  T2_TRY(gemm_rm(bl, false, false, (int)TB, kDRnn + kEnc, 81, w.dy, 81, m->projgate_w, kDRnn + kEnc, w.gproj, kDRnn + kEnc, 0.f));
   T2_CUDA(cudaFuncSetAttribute(att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   // T2_BWD_PROFILE=1: CUDA-event time per kernel class over the first 64 steps (stderr), for tuning
@@ -567,8 +582,8 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     {  // KA
       LstmBwdArgs k;
       memset(&k, 0, sizeof(k));
-      k.src0 = carry ? w.pb : nullptr; k.ld0 = kPBld; k.off0 = 1536;
-      k.vec = w.dy + (size_t)t * B * 81; k.nvec = 81; k.ldvec = 81; k.Wv = m->projgate_w; k.ldwv = kDRnn + kEnc;
+      k.src0 = carry ? w.pb : nullptr; k.ld0 = kPBld; k.off0 = 1536; k.ns0 = kSplitB;
+      k.add = w.gproj + (size_t)t * B * 1536; k.ldadd = 1536;
       k.keep = a->dec_keep ? a->dec_keep + (size_t)t * B * kDRnn : nullptr;
       k.dropout = training; k.seed = a->seed; k.site = (uint32_t)(t * 4 + 3); k.p = p_dec;
       k.gates = st.gd + (size_t)t * B * 4096; k.c = st.cd + (size_t)(t + 1) * B * kDRnn; k.c_prev = st.cd + (size_t)t * B * kDRnn;
@@ -582,8 +597,8 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       k.A = w.dgd + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
       k.W0 = m->w[W_DRNN_WIH]; k.ldw0 = kARnn + kEnc; k.cols0 = kARnn + kEnc;
       k.W1 = m->w[W_DRNN_WHH]; k.ldw1 = kDRnn; k.cols1 = kDRnn;
-      k.P = w.pb; k.ldp = kPBld;
-      skinny_nn_kernel<<<dim3(kPBld / 128, kSplit), 256, 0, s>>>(k);
+      k.P = w.pb; k.ldp = kPBld; k.nsplit = kSplitB;
+      skinny_nn_kernel<<<dim3(kPBld / 128, kSplitB), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
     T2_TICK(2);
@@ -593,7 +608,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       k.t = t; k.T = T; k.B = B; k.Te = Te; k.carry = carry; k.len = a->memory_lengths;
       k.memory = a->memory; k.pm = w.pm; k.q = w.q; k.v = m->w[W_ATT_V]; k.weff = w.weff;
       k.align = a->align; k.awc = w.awc; k.d_align = a->d_align;
-      k.PE = w.pe; k.PB = w.pb; k.dY = w.dy; k.wpg = m->projgate_w;
+      k.PE = w.pe; k.PB = w.pb; k.gproj = w.gproj; k.weffT = w.weffT;
       k.dctx = w.dctx; k.dx2 = a->d_prenet; k.dq = w.dq; k.gs = w.gs; k.gcat = w.gcat; k.cacc = w.cacc; k.dv = w.dv;
       att_bwd_kernel<<<dim3(2, B), 256, smem, s>>>(k);
       T2_LAUNCH_CHECK();
@@ -602,8 +617,8 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     {  // KD
       LstmBwdArgs k;
       memset(&k, 0, sizeof(k));
-      k.src0 = carry ? w.pe : nullptr; k.ld0 = kPEld; k.off0 = 768;
-      k.src1 = w.pb; k.ld1 = kPBld; k.off1 = 0;
+      k.src0 = carry ? w.pe : nullptr; k.ld0 = kPEld; k.off0 = 768; k.ns0 = kSplitE;
+      k.src1 = w.pb; k.ld1 = kPBld; k.off1 = 0; k.ns1 = kSplitB;
       k.vec = w.dq + (size_t)t * B * 128; k.nvec = 128; k.ldvec = 128; k.Wv = m->w[W_ATT_QUERY]; k.ldwv = kARnn;
       k.keep = a->att_keep ? a->att_keep + (size_t)t * B * kARnn : nullptr;
       k.dropout = training; k.seed = a->seed; k.site = (uint32_t)(t * 4 + 2); k.p = p_att;
@@ -618,8 +633,8 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       k.A = w.dga + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
       k.W0 = m->w[W_ARNN_WIH]; k.ldw0 = kPre + kEnc; k.cols0 = kPre + kEnc;
       k.W1 = m->w[W_ARNN_WHH]; k.ldw1 = kARnn; k.cols1 = kARnn;
-      k.P = w.pe; k.ldp = kPEld;
-      skinny_nn_kernel<<<dim3(kPEld / 128, kSplit), 256, 0, s>>>(k);
+      k.P = w.pe; k.ldp = kPEld; k.nsplit = kSplitE;
+      skinny_nn_kernel<<<dim3(kPEld / 128, kSplitE), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
     T2_TICK(5);

@@ -47,40 +47,49 @@ __global__ void embed_to_padded_kernel(const int64_t* __restrict__ text, const f
 }
 
 // ---- BatchNorm statistics over the valid rows (training) or running statistics (eval) ----------------
-// stats[0..C) = mean of z (without the conv bias), stats[C..2C) = 1/sqrt(var + eps)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int B, int T, int C, float eps,
-                                                       const float* __restrict__ cbias, float* run_mean, float* run_var,
-                                                       int training, float* __restrict__ stats) {
+// stats[0..C) = mean of z (without the conv bias), stats[C..2C) = 1/sqrt(var + eps).
+// Column reductions run as (C / 32) x kRedSplit blocks writing partial sums, then a small finalize kernel.
+constexpr int kRedSplit = 64;
+// mode 0: sum z ; mode 1: sum (z - mean)^2 with mean = stats[c]
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, int B, int T, int C, int mode,
+                                                         const float* __restrict__ stats, float* __restrict__ partial) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const long M = (long)B * T;
-  if (!training) {   // eval: normalise (z + bias) with the running statistics
-    if (rg == 0 && c < C) { stats[c] = run_mean[c] - cbias[c]; stats[C + c] = rsqrtf(run_var[c] + eps); }
-    return;
-  }
+  const long per = (M + kRedSplit - 1) / kRedSplit;
+  const long r0 = blockIdx.y * per, r1 = r0 + per < M ? r0 + per : M;
   float s = 0.f;
-  if (c < C) for (long r = rg; r < M; r += 8) { const int b = (int)(r / T), t = (int)(r % T); s += z[d_prow(b, t, T) * C + c]; }
+  if (c < C) {
+    const float mean = mode ? stats[c] : 0.f;
+    for (long r = r0 + rg; r < r1; r += 8) {
+      const int b = (int)(r / T), t = (int)(r % T);
+      const float d = z[d_prow(b, t, T) * C + c] - mean;
+      s += mode ? d * d : d;
+    }
+  }
   red[rg][cl] = s;
   __syncthreads();
-  float mean = 0.f;
-  for (int i = 0; i < 8; ++i) mean += red[i][cl];
-  mean /= (float)M;
-  __syncthreads();
-  float q = 0.f;
-  if (c < C) for (long r = rg; r < M; r += 8) { const int b = (int)(r / T), t = (int)(r % T); const float d = z[d_prow(b, t, T) * C + c] - mean; q = fmaf(d, d, q); }
-  red[rg][cl] = q;
-  __syncthreads();
   if (rg == 0 && c < C) {
-    float var = 0.f;
-    for (int i = 0; i < 8; ++i) var += red[i][cl];
-    var /= (float)M;
-    stats[c] = mean;
-    stats[C + c] = 1.f / sqrtf(var + eps);
-    if (run_mean) {   // nn.BatchNorm1d: momentum 0.1, unbiased variance
-      run_mean[c] = 0.9f * run_mean[c] + 0.1f * (mean + cbias[c]);
-      run_var[c] = 0.9f * run_var[c] + 0.1f * var * ((float)M / (float)(M > 1 ? M - 1 : 1));
-    }
+    float a = 0.f;
+    for (int i = 0; i < 8; ++i) a += red[i][cl];
+    partial[(long)blockIdx.y * C + c] = a;
+  }
+}
+// mode 0: mean ; mode 1: rstd (+ running statistics) ; mode 2: eval (running statistics -> stats)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int C, long M, float eps, const float* __restrict__ cbias,
+                                   float* run_mean, float* run_var, int mode, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (mode == 2) { stats[c] = run_mean[c] - cbias[c]; stats[C + c] = 1.f / sqrtf(run_var[c] + eps); return; }
+  double a = 0.0;
+  for (int i = 0; i < kRedSplit; ++i) a += (double)partial[(long)i * C + c];
+  if (mode == 0) { stats[c] = (float)(a / (double)M); return; }
+  const float var = (float)(a / (double)M);
+  stats[C + c] = 1.f / sqrtf(var + eps);
+  if (run_mean) {   // nn.BatchNorm1d: momentum 0.1, unbiased variance
+    run_mean[c] = 0.9f * run_mean[c] + 0.1f * (stats[c] + cbias[c]);
+    run_var[c] = 0.9f * run_var[c] + 0.1f * var * ((float)M / (float)(M > 1 ? M - 1 : 1));
   }
 }
 
@@ -123,15 +132,17 @@ __device__ __forceinline__ float g_ybn_at(const float* g, int g_padded, const fl
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ g, int g_padded, const float* __restrict__ y,
                                                             const float* __restrict__ z, const float* __restrict__ stats, int B, int T,
                                                             int C, int act, int dropout, const uint8_t* keep, uint64_t seed,
-                                                            uint32_t site, float* __restrict__ sums) {
+                                                            uint32_t site, float* __restrict__ partial) {
   __shared__ float r1[8][33], r2[8][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const long M = (long)B * T;
+  const long per = (M + kRedSplit - 1) / kRedSplit;
+  const long q0 = blockIdx.y * per, q1 = q0 + per < M ? q0 + per : M;
   float s1 = 0.f, s2 = 0.f;
   if (c < C) {
     const float mean = stats[c], rstd = stats[C + c];
-    for (long r = rg; r < M; r += 8) {
+    for (long r = q0 + rg; r < q1; r += 8) {
       const int b = (int)(r / T), t = (int)(r % T);
       const float gy = g_ybn_at(g, g_padded, y, b, t, c, C, T, act, dropout, keep, seed, site);
       s1 += gy;
@@ -143,8 +154,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   if (rg == 0 && c < C) {
     float a1 = 0.f, a2 = 0.f;
     for (int i = 0; i < 8; ++i) { a1 += r1[i][cl]; a2 += r2[i][cl]; }
-    sums[c] = a1; sums[C + c] = a2;     // = d beta, d gamma
+    partial[((long)blockIdx.y * 2 + 0) * C + c] = a1;
+    partial[((long)blockIdx.y * 2 + 1) * C + c] = a2;
   }
+}
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int C, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // sums[0..C) = d beta, sums[C..2C) = d gamma
+  if (i >= 2 * C) return;
+  const int which = i / C, c = i - which * C;
+  double a = 0.0;
+  for (int k = 0; k < kRedSplit; ++k) a += (double)partial[((long)k * 2 + which) * C + c];
+  sums[i] = (float)a;
 }
 // pass 2: g_z = gamma rstd (g_ybn - s1/M - xhat s2/M)  (training)  |  gamma rstd g_ybn  (eval), valid rows of a zeroed buffer
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int g_padded, const float* __restrict__ y, const float* __restrict__ z,
@@ -234,16 +254,28 @@ struct ConvLayer {
 };
 
 int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* xp, float* zp,
-             float* stats, float* yp, float* y_plain, bool update_running, cudaStream_t s) {
+             float* stats, float* yp, float* y_plain, bool update_running, float* partial, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
   for (int k = 0; k < kConvK; ++k)
     T2_TRY(gemm_rm(bl, false, true, Me, L.cout, L.cin, xp + (long)k * L.cin, L.cin, L.wpk + (long)k * L.cin, (long)kConvK * L.cin,
                    zp + (long)kPadRows * L.cout, L.cout, k ? 1.f : 0.f));
-  bn_stats_kernel<<<(L.cout + 31) / 32, 256, 0, s>>>(zp, B, T, L.cout, m->cfg.bn_eps, m->w[L.wbase + 1],
-                                                      update_running || !training ? const_cast<float*>(m->w[L.wbase + 4]) : nullptr,
-                                                      const_cast<float*>(m->w[L.wbase + 5]), training, stats);
-  T2_LAUNCH_CHECK();
+  {
+    float* rm = const_cast<float*>(m->w[L.wbase + 4]); float* rv = const_cast<float*>(m->w[L.wbase + 5]);
+    const long M = (long)B * T;
+    if (!training) {
+      bn_finalize_kernel<<<(L.cout + 127) / 128, 128, 0, s>>>(nullptr, L.cout, M, m->cfg.bn_eps, m->w[L.wbase + 1], rm, rv, 2, stats);
+      T2_LAUNCH_CHECK();
+    } else {
+      for (int mode = 0; mode < 2; ++mode) {
+        bn_partial_kernel<<<dim3((L.cout + 31) / 32, kRedSplit), 256, 0, s>>>(zp, B, T, L.cout, mode, stats, partial);
+        T2_LAUNCH_CHECK();
+        bn_finalize_kernel<<<(L.cout + 127) / 128, 128, 0, s>>>(partial, L.cout, M, m->cfg.bn_eps, m->w[L.wbase + 1],
+                                                                update_running ? rm : nullptr, rv, mode, stats);
+        T2_LAUNCH_CHECK();
+      }
+    }
+  }
   const long n = (long)B * T * L.cout;
   bn_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(zp, stats, m->w[L.wbase + 2], m->w[L.wbase + 3], B, T, L.cout, L.act,
                                                              L.dropout, L.keep, seed, L.site, yp, y_plain);
@@ -258,7 +290,11 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
              const float* ones, float* const* G, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
-  bn_bwd_reduce_kernel<<<(L.cout + 31) / 32, 256, 0, s>>>(g, g_padded, yp, zp, stats, B, T, L.cout, L.act, L.dropout, L.keep, seed, L.site, sums);
+  float* partial = sums + 2 * L.cout;      // (kRedSplit, 2, cout) scratch behind the two result rows
+  bn_bwd_reduce_kernel<<<dim3((L.cout + 31) / 32, kRedSplit), 256, 0, s>>>(g, g_padded, yp, zp, stats, B, T, L.cout, L.act, L.dropout,
+                                                                            L.keep, seed, L.site, partial);
+  T2_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<(2 * L.cout + 127) / 128, 128, 0, s>>>(partial, L.cout, sums);
   T2_LAUNCH_CHECK();
   T2_CUDA(cudaMemsetAsync(gz_p, 0, (size_t)Mp * L.cout * 4, s));
   const long n = (long)B * T * L.cout;
@@ -295,7 +331,7 @@ size_t stack_carve(char* base, int B, int T, int L, const int* ch, StackStash* s
   memset(&d, 0, sizeof(d));
   for (int l = 0; l <= L; ++l) { d.x[l] = (float*)p; p += a256(Mp * ch[l] * 4); }
   for (int l = 0; l < L; ++l) { d.z[l] = (float*)p; p += a256(Mp * ch[l + 1] * 4); }
-  for (int l = 0; l < L; ++l) { d.stats[l] = (float*)p; p += a256((size_t)2 * ch[l + 1] * 4); }
+  for (int l = 0; l < L; ++l) { d.stats[l] = (float*)p; p += a256((size_t)(2 + kRedSplit) * ch[l + 1] * 4); }   // + reduction scratch
   if (st) *st = d;
   return (size_t)(p - (uintptr_t)base);
 }
@@ -445,7 +481,8 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
   ConvLayer L[5];
   post_layers(m, a->training, a->keep, B, T, L);
   for (int i = 0; i < 5; ++i)
-    T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.x[i], st.z[i], st.stats[i], st.x[i + 1], nullptr, a->training != 0, s));
+    T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.x[i], st.z[i], st.stats[i], st.x[i + 1], nullptr, a->training != 0,
+                    st.stats[i] + 2 * L[i].cout, s));
   rows_to_bct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.x[5], a->add_residual ? st.x[0] : nullptr, a->mel_post, B, T, kMel);
   T2_LAUNCH_CHECK();
   return T2_OK;
@@ -454,7 +491,7 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
 size_t postnet_backward_ws_bytes(int B, int T) {
   const size_t Mp = (size_t)B * (T + 2 * kPadRows);
   return 3 * a256(Mp * kPost * 4) + a256((size_t)B * T * kMel * 4) + a256(Mp * 4) + a256((size_t)kPost * kPost * kConvK * 4) +
-         a256(2 * kPost * 4) + 1024;
+         a256((size_t)(2 + 2 * kRedSplit) * kPost * 4) + 1024;
 }
 
 int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
@@ -532,7 +569,7 @@ int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, cons
   enc_layers(m, a->training, a->keep, B, T, L);
   for (int i = 0; i < 3; ++i)
     T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], i == 2 ? st.xl : nullptr,
-                    a->training != 0, s));
+                    a->training != 0, st.cs.stats[i] + 2 * L[i].cout, s));
   *xl = st.xl; *gates = st.gates; *cst = st.cst;
   return T2_OK;
 }
@@ -549,7 +586,7 @@ size_t encoder_backward_ws_bytes(int B, int T) {
   constexpr int nsplit = 8;
   return a256((size_t)B * T * 8 * kEncH * 4) + a256((size_t)B * T * kEnc * 4) * 2 + a256((size_t)2 * nsplit * 64 * kEncH * 4) +
          a256((size_t)2 * 64 * kEncH * 4) + 3 * a256(Mp * kEnc * 4) + a256((Mp > (size_t)B * T ? Mp : (size_t)B * T) * 4) +
-         a256((size_t)kEnc * kEnc * kConvK * 4) + a256(2 * kEnc * 4) + a256(8 * kEncH * 4) + 2048;
+         a256((size_t)kEnc * kEnc * kConvK * 4) + a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4) + a256(8 * kEncH * 4) + 2048;
 }
 
 int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
@@ -574,7 +611,7 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   const size_t n_ones = Mp > (size_t)B * T ? Mp : (size_t)B * T;
   float* ones = (float*)p; p += a256(n_ones * 4);
   float* dwpk = (float*)p; p += a256((size_t)kEnc * kEnc * kConvK * 4);
-  float* sums = (float*)p; p += a256(2 * kEnc * 4);
+  float* sums = (float*)p; p += a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4);
   float* tmp = (float*)p;
   cublasHandle_t bl;
   T2_TRY(blas_handle(m, s, &bl));
