@@ -8,8 +8,8 @@
   available).  Differences from the reference, none visible to train.py:
     - gradients are flattened into size-bounded buckets in reverse registration order (postnet ->
       decoder -> encoder, the order in which backward produces them) instead of one 112.8 MB buffer,
-      and each bucket's all-reduce is launched asynchronously so it overlaps the remaining buckets'
-      flatten/copy work;
+      and a bucket's all-reduce is launched asynchronously as soon as its last gradient exists, so the
+      exchange overlaps the backward kernels of the earlier layers;
     - the hook is registered once per parameter even when apply_gradient_allreduce is called twice
       (train.py wraps at :79 and :179).
 """
@@ -80,21 +80,70 @@ def apply_gradient_allreduce(module, bucket_bytes=32 << 20):
         if torch.is_tensor(t):
             dist.broadcast(t, 0)
     module.needs_reduction = False
+    # Buckets in the order backward produces the gradients (postnet -> decoder -> encoder).  A bucket's all-reduce is
+    # launched (async, NCCL's own stream) as soon as its last gradient has been accumulated, so the exchange of the
+    # postnet / decoder gradients overlaps the backward kernels of the layers before them; the callback at the end of
+    # backward only waits and scatters the averaged values back (the reference reduces everything after backward).
+    params = [p for p in reversed(list(module.parameters())) if p.requires_grad]
+    buckets = list(_buckets(params, bucket_bytes))
+    where = {id(p): bi for bi, bucket in enumerate(buckets) for p in bucket}
+    state = {"remaining": [len(b_) for b_ in buckets], "pending": {}}
+
+    def launch(bi):
+        bucket = buckets[bi]
+        flat = torch.cat([p.grad.data.reshape(-1) for p in bucket])
+        state["pending"][bi] = (dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat)
 
     def reduce_now():
-        if module.needs_reduction:
-            module.needs_reduction = False
-            allreduce_gradients(module, bucket_bytes)
+        if not module.needs_reduction:
+            return
+        module.needs_reduction = False
+        world = dist.get_world_size()
+        late = []
+        for bi, bucket in enumerate(buckets):
+            if bi not in state["pending"]:
+                if all(p.grad is not None for p in bucket):
+                    launch(bi)
+                else:                                              # parameters that took no part in this backward
+                    late += [p for p in bucket if p.grad is not None]
+        for bi, (work, flat) in sorted(state["pending"].items()):
+            work.wait()
+            flat /= world
+            off = 0
+            for p in buckets[bi]:
+                n = p.numel()
+                p.grad.data.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        state["pending"] = {}
+        if late:
+            flat = torch.cat([p.grad.data.reshape(-1) for p in late])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat /= world
+            off = 0
+            for p in late:
+                n = p.numel()
+                p.grad.data.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
 
     def grad_hook(*unused):                                       # distributed.py:163-167
         torch.autograd.Variable._execution_engine.queue_callback(reduce_now)
 
-    for p in module.parameters():
-        if p.requires_grad:
-            p.register_hook(grad_hook)
+    def grad_ready(p):
+        if not module.needs_reduction:
+            return
+        bi = where[id(p)]
+        state["remaining"][bi] -= 1
+        if state["remaining"][bi] == 0:
+            launch(bi)
+
+    for p in params:
+        p.register_hook(grad_hook)
+        p.register_post_accumulate_grad_hook(grad_ready)
 
     def set_needs_reduction(self, inputs, output):                # distributed.py:169-172
         self.needs_reduction = True
+        state["remaining"] = [len(b_) for b_ in buckets]
+        state["pending"] = {}
 
     module.register_forward_hook(set_needs_reduction)
     module._t2_dp_wrapped = True
