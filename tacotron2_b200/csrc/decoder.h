@@ -62,4 +62,12 @@ size_t decoder_backward_ws_bytes(int B, int T_enc, int T_mel);
 int prenet_backward(T2Model* m, const T2PrenetBwdArgs* a, cudaStream_t s);
 bool persistent_supported(const T2Model* m, const T2DecoderArgs* a);
 
+// tensor-core skinny GEMMs of the decoder backward (decoder_persistent.cu): which = 0 decoder LSTM (2560 columns),
+// 1 attention LSTM (1792 columns); K = 4096 gate rows in kBwdGemmSplit partial sums
+constexpr int kBwdGemmSplit = 4;
+constexpr int kBwdImgBytes = 64 * 16384;     // activation image of one (64 x 4096) operand
+int bwd_gemm_prepare(T2Model* m, cudaStream_t s);
+int bwd_gemm_run(T2Model* m, int which, const uint8_t* x_img, const float* inv_scale, float* P, int ldp, DecoderCtrl* ctrl,
+                 cudaStream_t s);
+
 }  // namespace t2

@@ -17,6 +17,7 @@
 
 #include "decoder.h"
 #include "gemm_f32.cuh"
+#include "umma.cuh"
 
 namespace t2 {
 
@@ -76,6 +77,7 @@ struct LstmBwdArgs {
   const float* c; const float* c_prev;     // (B, 1024)
   float* g_c;                              // (B, 1024) carry, in/out
   float* dG;                               // (B, 4096) out
+  uint8_t* img; float* inv_scale;          // tensor-core path: scaled split-fp16 operand image of dG + 1/scale per row
 };
 
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs a) {
@@ -118,6 +120,79 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs a) {
   dg[2048] = d_c * gi * (1.f - gg * gg);
   dg[3072] = d_o * go * (1.f - go);
   a.g_c[(long)b * 1024 + unit] = d_c * gf;
+}
+
+// Same computation with one block per batch row (1024 threads = hidden units): the block knows the row maximum of
+// dG, scales the row by a power of two into [0.5, 1) and writes it as the split-fp16 operand image of the
+// tensor-core GEMM (gradients span many orders of magnitude; fp16 does not) next to the fp32 copy.
+__global__ void __launch_bounds__(1024) lstm_bwd_row_kernel(const LstmBwdArgs a) {
+  __shared__ float s_vec[128];
+  __shared__ float s_max[32];
+  const int b = blockIdx.x, unit = threadIdx.x;
+  for (int i = threadIdx.x; i < a.nvec; i += 1024) s_vec[i] = a.vec[(long)b * a.ldvec + i];
+  __syncthreads();
+  float g_h = a.add ? a.add[(long)b * a.ldadd + unit] : 0.f;
+  if (a.src0) {
+#pragma unroll 4
+    for (int s = 0; s < a.ns0; ++s) g_h += a.src0[((long)s * 64 + b) * a.ld0 + a.off0 + unit];
+  }
+  if (a.src1) {
+#pragma unroll 4
+    for (int s = 0; s < a.ns1; ++s) g_h += a.src1[((long)s * 64 + b) * a.ld1 + a.off1 + unit];
+  }
+  {
+    float p4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int o = 0; o < a.nvec; o += 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p4[i] = fmaf(s_vec[o + i], __ldg(a.Wv + (long)(o + i) * a.ldwv + unit), p4[i]);
+    }
+    g_h += (p4[0] + p4[1]) + (p4[2] + p4[3]);
+  }
+  if (a.dropout) {
+    const long idx = (long)b * 1024 + unit;
+    const bool keep = a.keep ? a.keep[idx] != 0 : philox_keep(a.seed, a.site, (uint64_t)idx, a.p);
+    g_h = keep ? g_h * (1.f / (1.f - a.p)) : 0.f;
+  }
+  const float* gp = a.gates + (long)b * 4096 + unit;
+  const float gi = gp[0], gf = gp[1024], gg = gp[2048], go = gp[3072];
+  const float c = a.c[(long)b * 1024 + unit], cp = a.c_prev[(long)b * 1024 + unit];
+  const float tc = tanhf(c);
+  const float d_o = g_h * tc;
+  const float d_c = a.g_c[(long)b * 1024 + unit] + g_h * go * (1.f - tc * tc);
+  float d[4];
+  d[0] = d_c * gg * gi * (1.f - gi);
+  d[1] = d_c * cp * gf * (1.f - gf);
+  d[2] = d_c * gi * (1.f - gg * gg);
+  d[3] = d_o * go * (1.f - go);
+  float* dg = a.dG + (long)b * 4096 + unit;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) dg[g * 1024] = d[g];
+  a.g_c[(long)b * 1024 + unit] = d_c * gf;
+  // row maximum -> power-of-two scale
+  float mx = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fmaxf(fabsf(d[2]), fabsf(d[3])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = s_max[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);           // mx = f * 2^e, f in [0.5, 1)
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  const float sc = ldexpf(1.f, -e);
+  if (threadIdx.x == 0) a.inv_scale[b] = ldexpf(1.f, e);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int k = g * 1024 + unit;
+    __half h, l;
+    split_fp16(d[g] * sc, h, l);
+    __half* hi = reinterpret_cast<__half*>(a.img + (size_t)(k >> 6) * 16384);
+    __half* lo = hi + 64 * kChunkK;
+    const uint32_t eo = img_elem_offset(b, k & 63);
+    hi[eo] = h; lo[eo] = l;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +284,7 @@ struct AttBwdArgs {
   const float* align; const float* awc;   // (B,T,Te) forward weights / cumulative weights BEFORE step t
   const float* d_align;                   // (B,T,Te) or null
   const float* PE; const float* PB;       // partials of step t+1 (KE) and of this step (KB)
+  int nsE, nsB;                           // number of partial sums in PE / PB
   const float* gproj;                     // (T,B,1536) = [d_mel_t ; d_gate_t] . W_PG, all steps (time batched)
   const float* weffT;                     // (62, 128) transposed fused location filter
   float* dctx; float* dx2; float* dq;     // (T,B,512), (T,B,256), (T,B,128)
@@ -261,18 +337,18 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   for (int c = tid; c < 512; c += 256) {
     float g = a.gproj[((long)t * B + b) * 1536 + 1024 + c];
     if (a.carry) {
-#pragma unroll
-      for (int s = 0; s < kSplitE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + 256 + c];
+#pragma unroll 5
+      for (int s = 0; s < a.nsE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + 256 + c];
     }
-#pragma unroll
-    for (int s = 0; s < kSplitB; ++s) g += a.PB[((long)s * 64 + b) * kPBld + 1024 + c];
+#pragma unroll 4
+    for (int s = 0; s < a.nsB; ++s) g += a.PB[((long)s * 64 + b) * kPBld + 1024 + c];
     s_ctx[c] = g;
     if (h == 0) a.dctx[((long)t * B + b) * 512 + c] = g;
   }
   if (h == 0 && a.carry) {   // gradient wrt the prenet output of step t+1 (first 256 columns of KE's result)
     float g = 0.f;
-#pragma unroll
-    for (int s = 0; s < kSplitE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
+#pragma unroll 5
+    for (int s = 0; s < a.nsE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
     a.dx2[((long)(t + 1) * B + b) * 256 + tid] = g;
   }
   __syncthreads();
@@ -459,11 +535,11 @@ __global__ void im2col_kernel(const float* __restrict__ align, const float* __re
   }
   cols[i] = v;
 }
-__global__ void reduce_pe_x2_kernel(const float* __restrict__ PE, float* __restrict__ dx2, int B) {
+__global__ void reduce_pe_x2_kernel(const float* __restrict__ PE, float* __restrict__ dx2, int B, int nsE) {
   const int b = blockIdx.x, c = threadIdx.x;   // step 0: g_x2 = sum of the partials
   if (b >= B) return;
   float g = 0.f;
-  for (int s = 0; s < kSplitE; ++s) g += PE[((long)s * 64 + b) * kPEld + c];
+  for (int s = 0; s < nsE; ++s) g += PE[((long)s * 64 + b) * kPEld + c];
   dx2[(long)b * 256 + c] = g;
 }
 __global__ void fill_kernel(float* p, float v, long n) {
@@ -485,7 +561,8 @@ __global__ void prenet_dz_kernel(const float* g, const float* __restrict__ act, 
 
 struct BwdWs {
   float *dga, *dgd, *q, *dq, *awc, *pm, *dpm, *dctx, *dy, *gs, *cols, *pb, *pe, *gdc, *gac, *cacc, *gcat, *dv, *ones, *weff,
-      *dweff, *tmp, *gproj, *weffT;
+      *dweff, *tmp, *gproj, *weffT, *inv_scale;
+  uint8_t *img_d, *img_a; DecoderCtrl* ctrl;
 };
 size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   uintptr_t p = (uintptr_t)base;
@@ -507,6 +584,11 @@ size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   d.weff = take((size_t)kAtt * kTaps); d.dweff = take((size_t)kAtt * kColsLd);
   d.tmp = take(4096);
   d.gproj = take(TB * 1536); d.weffT = take((size_t)kAtt * kTaps);
+  d.inv_scale = take(128);
+  d.img_d = (uint8_t*)take(kBwdImgBytes / 4 + 256); d.img_a = (uint8_t*)take(kBwdImgBytes / 4 + 256);
+  d.img_d = (uint8_t*)(((uintptr_t)d.img_d + 1023) & ~(uintptr_t)1023);
+  d.img_a = (uint8_t*)(((uintptr_t)d.img_a + 1023) & ~(uintptr_t)1023);
+  d.ctrl = (DecoderCtrl*)take(sizeof(DecoderCtrl) / 4 + 64);
   if (w) *w = d;
   return (size_t)(p - (uintptr_t)base);
 }
@@ -575,6 +657,21 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
   do {                                                                \
     if (prof && T - 1 - t < kProfSteps) cudaEventRecord(pev[T - 1 - t][i], s); \
   } while (0)
+  // skinny GEMMs: tcgen05 split-fp16 engine (default) or the fp32 SIMT kernel (T2_BWD_GEMM=simt, cross-check)
+  bool tc_gemm = true;
+  {
+    const char* e = getenv("T2_BWD_GEMM");
+    if (e && e[0] == 's') tc_gemm = false;
+  }
+  const int nsB = tc_gemm ? kBwdGemmSplit : kSplitB, nsE = tc_gemm ? kBwdGemmSplit : kSplitE;
+  if (tc_gemm) {
+    T2_TRY(bwd_gemm_prepare(m, s));
+    T2_CUDA(cudaMemsetAsync(w.img_d, 0, kBwdImgBytes, s));      // rows >= B stay zero
+    T2_CUDA(cudaMemsetAsync(w.img_a, 0, kBwdImgBytes, s));
+    T2_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(DecoderCtrl), s));
+    fill_kernel<<<1, 128, 0, s>>>(w.inv_scale, 1.f, 128);
+    T2_LAUNCH_CHECK();
+  }
   // ---- phase 1: reverse-time recurrence ---------------------------------------------------------------
   for (int t = T - 1; t >= 0; --t) {
     T2_TICK(0);
@@ -582,16 +679,21 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     {  // KA
       LstmBwdArgs k;
       memset(&k, 0, sizeof(k));
-      k.src0 = carry ? w.pb : nullptr; k.ld0 = kPBld; k.off0 = 1536; k.ns0 = kSplitB;
+      k.src0 = carry ? w.pb : nullptr; k.ld0 = kPBld; k.off0 = 1536; k.ns0 = nsB;
       k.add = w.gproj + (size_t)t * B * 1536; k.ldadd = 1536;
+      k.img = w.img_d; k.inv_scale = w.inv_scale;
       k.keep = a->dec_keep ? a->dec_keep + (size_t)t * B * kDRnn : nullptr;
       k.dropout = training; k.seed = a->seed; k.site = (uint32_t)(t * 4 + 3); k.p = p_dec;
       k.gates = st.gd + (size_t)t * B * 4096; k.c = st.cd + (size_t)(t + 1) * B * kDRnn; k.c_prev = st.cd + (size_t)t * B * kDRnn;
       k.g_c = w.gdc; k.dG = w.dgd + (size_t)t * B * 4096;
-      lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
+      if (tc_gemm) lstm_bwd_row_kernel<<<B, 1024, 0, s>>>(k);
+      else lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
     T2_TICK(1);
+    if (tc_gemm) {
+      T2_TRY(bwd_gemm_run(m, 0, w.img_d, w.inv_scale, w.pb, kPBld, w.ctrl, s));
+    } else
     {  // KB
       SkinnyArgs k;
       k.A = w.dgd + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
@@ -608,7 +710,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       k.t = t; k.T = T; k.B = B; k.Te = Te; k.carry = carry; k.len = a->memory_lengths;
       k.memory = a->memory; k.pm = w.pm; k.q = w.q; k.v = m->w[W_ATT_V]; k.weff = w.weff;
       k.align = a->align; k.awc = w.awc; k.d_align = a->d_align;
-      k.PE = w.pe; k.PB = w.pb; k.gproj = w.gproj; k.weffT = w.weffT;
+      k.PE = w.pe; k.PB = w.pb; k.nsE = nsE; k.nsB = nsB; k.gproj = w.gproj; k.weffT = w.weffT;
       k.dctx = w.dctx; k.dx2 = a->d_prenet; k.dq = w.dq; k.gs = w.gs; k.gcat = w.gcat; k.cacc = w.cacc; k.dv = w.dv;
       att_bwd_kernel<<<dim3(2, B), 256, smem, s>>>(k);
       T2_LAUNCH_CHECK();
@@ -617,17 +719,22 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     {  // KD
       LstmBwdArgs k;
       memset(&k, 0, sizeof(k));
-      k.src0 = carry ? w.pe : nullptr; k.ld0 = kPEld; k.off0 = 768; k.ns0 = kSplitE;
-      k.src1 = w.pb; k.ld1 = kPBld; k.off1 = 0; k.ns1 = kSplitB;
+      k.src0 = carry ? w.pe : nullptr; k.ld0 = kPEld; k.off0 = 768; k.ns0 = nsE;
+      k.src1 = w.pb; k.ld1 = kPBld; k.off1 = 0; k.ns1 = nsB;
+      k.img = w.img_a; k.inv_scale = w.inv_scale + 64;
       k.vec = w.dq + (size_t)t * B * 128; k.nvec = 128; k.ldvec = 128; k.Wv = m->w[W_ATT_QUERY]; k.ldwv = kARnn;
       k.keep = a->att_keep ? a->att_keep + (size_t)t * B * kARnn : nullptr;
       k.dropout = training; k.seed = a->seed; k.site = (uint32_t)(t * 4 + 2); k.p = p_att;
       k.gates = st.ga + (size_t)t * B * 4096; k.c = st.ca + (size_t)(t + 1) * B * kARnn; k.c_prev = st.ca + (size_t)t * B * kARnn;
       k.g_c = w.gac; k.dG = w.dga + (size_t)t * B * 4096;
-      lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
+      if (tc_gemm) lstm_bwd_row_kernel<<<B, 1024, 0, s>>>(k);
+      else lstm_bwd_kernel<<<dim3(4, B), 256, 0, s>>>(k);
       T2_LAUNCH_CHECK();
     }
     T2_TICK(4);
+    if (tc_gemm) {
+      T2_TRY(bwd_gemm_run(m, 1, w.img_a, w.inv_scale + 64, w.pe, kPEld, w.ctrl, s));
+    } else
     {  // KE
       SkinnyArgs k;
       k.A = w.dga + (size_t)t * B * 4096; k.lda = 4096; k.rows = B; k.nred = 4096;
@@ -640,7 +747,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     T2_TICK(5);
   }
   if (prof) cudaEventRecord(ph[1], s);
-  reduce_pe_x2_kernel<<<B, 256, 0, s>>>(w.pe, a->d_prenet, B);
+  reduce_pe_x2_kernel<<<B, 256, 0, s>>>(w.pe, a->d_prenet, B, nsE);
   T2_LAUNCH_CHECK();
 
   // ---- phase 2: time-batched gradients --------------------------------------------------------------------

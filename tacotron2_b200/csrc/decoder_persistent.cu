@@ -75,6 +75,12 @@ struct CtaPlan {
   EventPlan ev[kNumEvents];
 };
 
+struct BwdCta {          // one CTA of a backward skinny GEMM: a tile of output columns x a range of K chunks
+  EventPlan ep;
+  int32_t chunk0, nchunks;   // K chunks (64 gate rows each) of this CTA
+  int32_t col0, split;       // first output column, index of the K split (partials)
+};
+
 struct PersistentPack {
   uint8_t* wimg = nullptr; size_t wimg_bytes = 0;
   CtaPlan* plans = nullptr;           // device, kG entries
@@ -85,6 +91,9 @@ struct PersistentPack {
   int32_t* rows = nullptr;            // row tables for packing
   float* weff = nullptr;              // (128, 64) fp32 fused location filter W_ld . W_loc (62 taps + 2 zero)
   uint8_t* weff_img = nullptr;        // its split-fp16 operand image (32 KiB)
+  // backward skinny GEMMs (training): W^T images of [W_ih | W_hh] of the decoder (0) and attention (1) LSTM
+  uint8_t* bwd_wimg[2] = {nullptr, nullptr};
+  struct BwdCta* bwd_plans[2] = {nullptr, nullptr};
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1100,6 +1109,7 @@ void persistent_pack_destroy(T2Model* m) {
   if (!pk) return;
   cudaFree(pk->wimg); cudaFree(pk->plans); cudaFree(pk->wp_all); cudaFree(pk->bias_p);
   cudaFree(pk->bias_a); cudaFree(pk->bias_d); cudaFree(pk->rows); cudaFree(pk->weff); cudaFree(pk->weff_img);
+  for (int i = 0; i < 2; ++i) { cudaFree(pk->bwd_wimg[i]); cudaFree(pk->bwd_plans[i]); }
   delete pk;
   m->pk = nullptr;
 }
@@ -1309,6 +1319,154 @@ int selftest_umma(const float* A, const float* W, int N, int K, int passes, floa
   T2_LAUNCH_CHECK();
   T2_CUDA(cudaStreamSynchronize(s));
   cudaFree(ximg); cudaFree(wimg); cudaFree(ctrl);
+  return T2_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Backward skinny GEMMs of the training path on the tensor cores (decoder_backward.cu, KB / KE):
+//   P[split][b][col] = inv_scale[b] * sum_{n in the split's chunks} dG_scaled[b][n] * Wcat[n][col]
+// dG (64 x 4096) arrives as a split-fp16 activation image whose rows were scaled by a power of two
+// (row maximum in [0.5, 1): gradients span many orders of magnitude, fp16 does not); Wcat = [W_ih | W_hh]
+// is streamed as W^T images (rows = output columns, K = gate rows).  Same ring / MMA / accumulator read-out
+// as the forward events (run_event): M = 128 stacked [X_hi ; X_lo], one MMA per 16-wide K step.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kBwdTileB = 80, kBwdTileE = 64;       // output columns per CTA: 2560 = 32 x 80, 1792 = 28 x 64
+
+__global__ void pack_bwd_wimg_kernel(const float* __restrict__ w0, int cols0, const float* __restrict__ w1, int cols1,
+                                     const BwdCta* __restrict__ plans, uint8_t* __restrict__ wimg) {
+  // grid (max chunks per CTA, n_cta): image block of chunk j of CTA c: rows = its output columns, k = 64 gate rows
+  const BwdCta& pc = plans[blockIdx.y];
+  const int j = blockIdx.x;
+  if (j >= pc.nchunks) return;
+  const int n = pc.ep.nrows;
+  __half* hi = reinterpret_cast<__half*>(wimg + pc.ep.w_off + (size_t)j * pc.ep.w_bytes);
+  __half* lo = hi + n * kChunkK;
+  const int n0 = (pc.chunk0 + j) * kChunkK;
+  for (int i = threadIdx.x; i < n * kChunkK; i += blockDim.x) {
+    const int k = i / n, r = i - k * n;            // r fastest: coalesced along the weight matrix' columns
+    const int col = pc.col0 + r;
+    const float v = col < cols0 ? w0[(long)(n0 + k) * cols0 + col] : w1[(long)(n0 + k) * cols1 + (col - cols0)];
+    __half h, l;
+    split_fp16(v, h, l);
+    const uint32_t e = img_elem_offset(r, k);
+    hi[e] = h; lo[e] = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_gemm_kernel(const uint8_t* __restrict__ x_img, const uint8_t* __restrict__ w_img, const BwdCta* __restrict__ plans,
+                const float* __restrict__ inv_scale, float* __restrict__ P, int ldp, DecoderCtrl* ctrl) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BwdCta pc = plans[blockIdx.x];
+  uint8_t* sp = smem_raw;
+  Ring rg;
+  rg.stage0 = sp; sp += kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
+  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
+  float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
+  rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
+  rg.pol_x = ptx::policy_evict_last(); rg.pol_w = ptx::policy_evict_first();
+  rg.cs = 1; rg.rank = 0; rg.pre = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
+    ptx::mbar_init(rg.acc, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int quad = warp & 3, cg = warp >> 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  for (int c = cg * 40; c < cg * 40 + 40; c += 8) ptx::tmem_zero8(t_lane + c);
+  ptx::tmem_wait_st();
+  ptx::tc_fence_before();
+  __syncthreads();
+  run_event(rg, pc.ep, x_img + (size_t)pc.chunk0 * kXChunkBytes, w_img, pc.nchunks, tmem_base, ctrl, nullptr);
+  const int N = pc.ep.nrows;
+  const int row = (quad & 1) * 32 + lane;
+  float g[kHiCols / 32 + 1][8];
+  for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
+    acc_take8(t_lane, 0, N, c0, g[c0 / 32]);
+    if (quad >= 2)
+      for (int j = 0; j < 8; ++j) s_xch[row * kHiCols + c0 + j] = g[c0 / 32][j];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (quad < 2) {
+    const float sc = inv_scale[row];
+    float* out = P + ((size_t)pc.split * kRows + row) * ldp + pc.col0;
+    for (int c0 = cg * 8; c0 < N; c0 += 8 * (kWarps / 4)) {
+      float4 v0, v1;
+      v0.x = (g[c0 / 32][0] + s_xch[row * kHiCols + c0 + 0]) * sc; v0.y = (g[c0 / 32][1] + s_xch[row * kHiCols + c0 + 1]) * sc;
+      v0.z = (g[c0 / 32][2] + s_xch[row * kHiCols + c0 + 2]) * sc; v0.w = (g[c0 / 32][3] + s_xch[row * kHiCols + c0 + 3]) * sc;
+      v1.x = (g[c0 / 32][4] + s_xch[row * kHiCols + c0 + 4]) * sc; v1.y = (g[c0 / 32][5] + s_xch[row * kHiCols + c0 + 5]) * sc;
+      v1.z = (g[c0 / 32][6] + s_xch[row * kHiCols + c0 + 6]) * sc; v1.w = (g[c0 / 32][7] + s_xch[row * kHiCols + c0 + 7]) * sc;
+      *reinterpret_cast<float4*>(out + c0) = v0;
+      *reinterpret_cast<float4*>(out + c0 + 4) = v1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+size_t bwd_gemm_smem() { return (size_t)kStages * kStageBytes + 16 * 8 + 16 + (size_t)kRows * kHiCols * 4 + 64; }
+}  // namespace
+
+int bwd_gemm_ctas(int which) { return which == 0 ? (2560 / kBwdTileB) * kBwdGemmSplit : (1792 / kBwdTileE) * kBwdGemmSplit; }
+
+// (re)builds the W^T images of both LSTMs from the caller's current fp32 weights (once per backward call)
+int bwd_gemm_prepare(T2Model* m, cudaStream_t s) {
+  PersistentPack* pk = (PersistentPack*)m->pk;
+  if (!pk) return fail(T2_ERR_INVALID, "backward GEMM: model has no persistent pack");
+  for (int which = 0; which < 2; ++which) {
+    const int tile = which == 0 ? kBwdTileB : kBwdTileE;
+    const int cols = which == 0 ? 2560 : 1792;
+    const int ntile = cols / tile, ncta = ntile * kBwdGemmSplit;
+    const int chunks = 4 * kARnn / kChunkK;                    // 64 K chunks
+    const uint32_t w_bytes = (uint32_t)(2 * tile * kChunkK * 2);
+    if (!pk->bwd_plans[which]) {
+      std::vector<BwdCta> plans(ncta);
+      for (int t = 0; t < ntile; ++t)
+        for (int sp = 0; sp < kBwdGemmSplit; ++sp) {
+          BwdCta& c = plans[t * kBwdGemmSplit + sp];
+          memset(&c, 0, sizeof(c));
+          c.chunk0 = sp * chunks / kBwdGemmSplit; c.nchunks = (sp + 1) * chunks / kBwdGemmSplit - c.chunk0;
+          c.col0 = t * tile; c.split = sp;
+          c.ep.nrows = tile; c.ep.col0 = 0; c.ep.ncons = 1; c.ep.n[0] = tile; c.ep.w_bytes = w_bytes;
+          c.ep.w_off = (uint32_t)(((size_t)t * chunks + c.chunk0) * w_bytes);
+        }
+      T2_CUDA(cudaMalloc((void**)&pk->bwd_plans[which], sizeof(BwdCta) * ncta));
+      T2_CUDA(cudaMemcpyAsync(pk->bwd_plans[which], plans.data(), sizeof(BwdCta) * ncta, cudaMemcpyHostToDevice, s));
+      T2_CUDA(cudaStreamSynchronize(s));
+      T2_CUDA(cudaMalloc((void**)&pk->bwd_wimg[which], (size_t)ntile * chunks * w_bytes));
+    }
+    const float* w0 = m->w[which == 0 ? W_DRNN_WIH : W_ARNN_WIH];
+    const float* w1 = m->w[which == 0 ? W_DRNN_WHH : W_ARNN_WHH];
+    const int cols0 = which == 0 ? kARnn + kEnc : kPre + kEnc;
+    pack_bwd_wimg_kernel<<<dim3(chunks / kBwdGemmSplit, ncta), 256, 0, s>>>(w0, cols0, w1, kARnn, pk->bwd_plans[which], pk->bwd_wimg[which]);
+    T2_LAUNCH_CHECK();
+  }
+  return T2_OK;
+}
+
+int bwd_gemm_run(T2Model* m, int which, const uint8_t* x_img, const float* inv_scale, float* P, int ldp, DecoderCtrl* ctrl,
+                 cudaStream_t s) {
+  PersistentPack* pk = (PersistentPack*)m->pk;
+  const size_t smem = bwd_gemm_smem();
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2_CUDA(cudaFuncSetAttribute(bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  bwd_gemm_kernel<<<bwd_gemm_ctas(which), kThreads, smem, s>>>(x_img, pk->bwd_wimg[which], pk->bwd_plans[which], inv_scale, P, ldp, ctrl);
+  T2_LAUNCH_CHECK();
   return T2_OK;
 }
 

@@ -46,9 +46,12 @@ def oracle_decoder_grads(sd, memory, mels, lens, pk, ak, dk, d_mel, d_gate, d_al
     return (mel.detach(), gate.detach(), align.detach()), {k: sdg[k].grad for k in names}, mem.grad
 
 
+@pytest.mark.parametrize("gemm", ["tc", "simt"])
 @pytest.mark.parametrize("B,Te,T,training,use_align", [(3, 19, 7, True, False), (5, 40, 12, True, True),
                                                        (4, 150, 9, False, False), (64, 33, 5, True, False)])
-def test_decoder_backward_vs_oracle_autograd(B, Te, T, training, use_align):
+def test_decoder_backward_vs_oracle_autograd(B, Te, T, training, use_align, gemm, monkeypatch):
+    """gemm: the reverse recurrence's skinny GEMMs on the tcgen05 split-fp16 engine (default) or the fp32 SIMT kernel."""
+    monkeypatch.setenv("T2_BWD_GEMM", gemm)
     sd = synth_state_dict(seed=21, scale=2.0)
     memory, mels, lens, pk, ak, dk, d_mel, d_gate, d_align = decoder_case(B, Te, T, seed=100 + B)
     if not use_align:
@@ -73,7 +76,7 @@ def test_decoder_backward_vs_oracle_autograd(B, Te, T, training, use_align):
         assert p.grad is not None, k
         errs[k] = rel_err(p.grad, ref_g["decoder." + k])
     bad = {k: v for k, v in errs.items() if not v < TOL}
-    print("decoder backward B=%d Te=%d T=%d: worst %.2e" % (B, Te, T, max(errs.values())))
+    print("decoder backward [%s] B=%d Te=%d T=%d: worst %.2e" % (gemm, B, Te, T, max(errs.values())))
     assert not bad, bad
 
 
