@@ -26,13 +26,25 @@ int blas_handle(T2Model* m, cudaStream_t s, cublasHandle_t* out) {
   if (!m->blas) {
     cublasHandle_t h;
     if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasCreate failed");
-    const char* e = getenv("T2_WGRAD_TF32");
-    cublasSetMathMode(h, (e && atoi(e)) ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH);
+    cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
     m->blas = h;
   }
   *out = (cublasHandle_t)m->blas;
   if (cublasSetStream(*out, s) != CUBLAS_STATUS_SUCCESS) return fail(T2_ERR_CUDA, "cublasSetStream failed");
   return T2_OK;
+}
+int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+            float* C, long ldc, float beta);
+// Weight-gradient GEMMs (reductions over all T x B rows): fp32 by default; T2_WGRAD_TF32=1 lets cuBLAS use TF32
+// tensor-core math for them (10-bit mantissa products, fp32 accumulation) -- an explicit opt-in.
+int gemm_rm_wgrad(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+                  float* C, long ldc, float beta) {
+  static int tf32 = -1;
+  if (tf32 < 0) { const char* e = getenv("T2_WGRAD_TF32"); tf32 = (e && atoi(e)) ? 1 : 0; }
+  if (tf32) cublasSetMathMode(h, CUBLAS_TF32_TENSOR_OP_MATH);
+  const int r = gemm_rm(h, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta);
+  if (tf32) cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+  return r;
 }
 // row-major C (M x N) = op(A) . op(B) + beta C;  ta: A is stored (K x M);  tb: B is stored (N x K)
 int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
@@ -294,7 +306,9 @@ struct AttBwdArgs {
   float* dv;                              // (B, 128) accumulated
 };
 
-__global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
+constexpr int kAttT = 512;               // threads of att_bwd_kernel: 16 warps hide the global-load latency
+constexpr int kAttG = kAttT / 64;         // position groups in steps (4), (5)
+__global__ void __launch_bounds__(kAttT) att_bwd_kernel(const AttBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -302,8 +316,8 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   const int TeP = Te + kLocK - 1;
   float* s_ctx = sm;                       // 512
   float* s_dy = s_ctx + 512;               // 96
-  float* s_red = s_dy + 96;                // 64 + 4 * 64 * 2
-  float* s_aw = s_red + 64 + 512;          // Te (padded to 4)
+  float* s_red = s_dy + 96;                // 64 + kAttG * 64 * 2
+  float* s_aw = s_red + 64 + kAttG * 128;          // Te (padded to 4)
   const int Te4 = (Te + 3) & ~3;
   float* s_ge = s_aw + Te4;                // Te
   float* s_pad0 = s_ge + Te4;              // TeP (+ slack)
@@ -314,9 +328,9 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   const int rd = (t + 1) & 1, wr = t & 1;
 
   // previous / cumulative attention weights of this step (zero padded by 15 each side)   model.py:358-360
-  for (int i = tid; i < TeP4; i += 256) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }
+  for (int i = tid; i < TeP4; i += kAttT) { s_pad0[i] = 0.f; s_pad1[i] = 0.f; }
   __syncthreads();
-  for (int j = tid; j < Te; j += 256) {
+  for (int j = tid; j < Te; j += kAttT) {
     s_pad0[15 + j] = t > 0 ? a.align[((long)b * T + t - 1) * Te + j] : 0.f;
     s_pad1[15 + j] = a.awc[((long)b * T + t) * Te + j];
     s_aw[j] = a.align[((long)b * T + t) * Te + j];
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     s_ge[j] = g;
   }
   // (1) total gradient wrt ctx_t: carry from step t+1's attention LSTM input, decoder LSTM input, projection
-  for (int c = tid; c < 512; c += 256) {
+  for (int c = tid; c < 512; c += kAttT) {
     float g = a.gproj[((long)t * B + b) * 1536 + 1024 + c];
     if (a.carry) {
 #pragma unroll 5
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     s_ctx[c] = g;
     if (h == 0) a.dctx[((long)t * B + b) * 512 + c] = g;
   }
-  if (h == 0 && a.carry) {   // gradient wrt the prenet output of step t+1 (first 256 columns of KE's result)
+  if (h == 0 && a.carry && tid < 256) {   // gradient wrt the prenet output of step t+1 (first 256 columns of KE's result)
     float g = 0.f;
 #pragma unroll 5
     for (int s = 0; s < a.nsE; ++s) g += a.PE[((long)s * 64 + b) * kPEld + tid];
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     float4 gc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) gc[i] = *reinterpret_cast<const float4*>(s_ctx + (i * 32 + lane) * 4);
-    for (int j0 = warp * 8; j0 < Te; j0 += 64) {
+    for (int j0 = warp * 8; j0 < Te; j0 += 8 * (kAttT / 32)) {
       float acc[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -381,15 +395,15 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   // (3) softmax backward: g_e = aw * (g_aw - sum_j aw g_aw)                              model.py:82
   {
     float p = 0.f;
-    for (int j = tid; j < Te; j += 256) p += s_aw[j] * s_ge[j];
+    for (int j = tid; j < Te; j += kAttT) p += s_aw[j] * s_ge[j];
     p = warp_sum(p);
     if (lane == 0) s_red[warp] = p;
     __syncthreads();
     float dot = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) dot += s_red[w];
+    for (int w = 0; w < kAttT / 32; ++w) dot += s_red[w];
     __syncthreads();
-    for (int j = tid; j < Te; j += 256) s_ge[j] = s_aw[j] * (s_ge[j] - dot);
+    for (int j = tid; j < Te; j += kAttT) s_ge[j] = s_aw[j] * (s_ge[j] - dot);
     __syncthreads();
   }
   // (4) recompute s = q + pa + pm, g_s = g_e v (1 - tanh^2 s); thread = (attention dim, group of positions)
@@ -401,7 +415,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     const float qv = a.q[((long)t * B + b) * 128 + ag];
     const float vv = __ldg(a.v + ag);
     float gq = 0.f, dv = 0.f;
-    for (int j0 = jg * 4; j0 < Te; j0 += 16) {
+    for (int j0 = jg * 4; j0 < Te; j0 += 4 * kAttG) {
       float pa[4] = {0.f, 0.f, 0.f, 0.f}, pmv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) pmv[i] = j0 + i < Te ? __ldg(a.pm + ((long)b * Te + j0 + i) * 128 + ag) : 0.f;
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     if (tid < 64) {
       float gq4 = 0.f, dv4 = 0.f;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { gq4 += s_red[64 + (g * 64 + tid) * 2]; dv4 += s_red[64 + (g * 64 + tid) * 2 + 1]; }
+      for (int g = 0; g < kAttG; ++g) { gq4 += s_red[64 + (g * 64 + tid) * 2]; dv4 += s_red[64 + (g * 64 + tid) * 2 + 1]; }
       a.dq[((long)t * B + b) * 128 + h * 64 + tid] = gq4;
       a.dv[(long)b * 128 + h * 64 + tid] += dv4;
     }
@@ -448,7 +462,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
     float wc[64];
 #pragma unroll
     for (int al = 0; al < 64; ++al) wc[al] = ck < kTaps ? __ldg(a.weff + (long)(h * 64 + al) * kTaps + ck) : 0.f;
-    for (int j = jg; j < Te; j += 4) {
+    for (int j = jg; j < Te; j += kAttG) {
       const float4* g4 = reinterpret_cast<const float4*>(s_gs + j * 64);
       float u = 0.f;
 #pragma unroll
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
   }
   __syncthreads();
   // (6) transposed location conv: g_cat[c][j'] = sum_k U[j' + 15 - k][c * 31 + k]        model.py:23
-  for (int i = tid; i < 2 * Te; i += 256) {
+  for (int i = tid; i < 2 * Te; i += kAttT) {
     const int c = i / Te, jp = i - c * Te;
     float g = 0.f;
     for (int k = 0; k < kLocK; ++k) {
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(256) att_bwd_kernel(const AttBwdArgs a) {
 
 size_t att_bwd_smem(int Te) {
   const int Te4 = (Te + 3) & ~3, TeP4 = (Te + kLocK - 1 + 7) & ~3;
-  return (size_t)(512 + 96 + 64 + 512 + 2 * Te4 + 2 * TeP4 + (size_t)Te4 * 64 + (size_t)Te * 65 + 16) * sizeof(float);
+  return (size_t)(512 + 96 + 64 + kAttG * 128 + 2 * Te4 + 2 * TeP4 + (size_t)Te4 * 64 + (size_t)Te * 65 + 16) * sizeof(float);
 }
 
 // ---- small helper kernels -------------------------------------------------------------------
@@ -712,7 +726,7 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
       k.align = a->align; k.awc = w.awc; k.d_align = a->d_align;
       k.PE = w.pe; k.PB = w.pb; k.nsE = nsE; k.nsB = nsB; k.gproj = w.gproj; k.weffT = w.weffT;
       k.dctx = w.dctx; k.dx2 = a->d_prenet; k.dq = w.dq; k.gs = w.gs; k.gcat = w.gcat; k.cacc = w.cacc; k.dv = w.dv;
-      att_bwd_kernel<<<dim3(2, B), 256, smem, s>>>(k);
+      att_bwd_kernel<<<dim3(2, B), kAttT, smem, s>>>(k);
       T2_LAUNCH_CHECK();
     }
     T2_TICK(3);
@@ -755,20 +769,20 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
   const float* x2 = a->teacher_prenet;
   const int TBi = (int)TB;
   if (G[W_ARNN_WIH]) {   // [x2_t | ctx_{t-1}]                                             model.py:352
-    T2_TRY(gemm_rm(bl, true, false, 4096, kPre, TBi, w.dga, 4096, x2, kPre, G[W_ARNN_WIH], kPre + kEnc, 0.f));
-    T2_TRY(gemm_rm(bl, true, false, 4096, kEnc, TBi, w.dga, 4096, st.ctx, kEnc, G[W_ARNN_WIH] + kPre, kPre + kEnc, 0.f));
+    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kPre, TBi, w.dga, 4096, x2, kPre, G[W_ARNN_WIH], kPre + kEnc, 0.f));
+    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dga, 4096, st.ctx, kEnc, G[W_ARNN_WIH] + kPre, kPre + kEnc, 0.f));
   }
-  if (G[W_ARNN_WHH]) T2_TRY(gemm_rm(bl, true, false, 4096, kARnn, TBi, w.dga, 4096, st.ha, kARnn, G[W_ARNN_WHH], kARnn, 0.f));
+  if (G[W_ARNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dga, 4096, st.ha, kARnn, G[W_ARNN_WHH], kARnn, 0.f));
   if (G[W_ARNN_BIH] || G[W_ARNN_BHH]) {
     T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dga, 4096, w.tmp, 4096, 0.f));
     if (G[W_ARNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
     if (G[W_ARNN_BHH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BHH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
   }
   if (G[W_DRNN_WIH]) {   // [ah_t | ctx_t]                                                 model.py:366-367
-    T2_TRY(gemm_rm(bl, true, false, 4096, kARnn, TBi, w.dgd, 4096, st.ha + (size_t)B * kARnn, kARnn, G[W_DRNN_WIH], kARnn + kEnc, 0.f));
-    T2_TRY(gemm_rm(bl, true, false, 4096, kEnc, TBi, w.dgd, 4096, st.ctx + (size_t)B * kEnc, kEnc, G[W_DRNN_WIH] + kARnn, kARnn + kEnc, 0.f));
+    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dgd, 4096, st.ha + (size_t)B * kARnn, kARnn, G[W_DRNN_WIH], kARnn + kEnc, 0.f));
+    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dgd, 4096, st.ctx + (size_t)B * kEnc, kEnc, G[W_DRNN_WIH] + kARnn, kARnn + kEnc, 0.f));
   }
-  if (G[W_DRNN_WHH]) T2_TRY(gemm_rm(bl, true, false, 4096, kDRnn, TBi, w.dgd, 4096, st.hd, kDRnn, G[W_DRNN_WHH], kDRnn, 0.f));
+  if (G[W_DRNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kDRnn, TBi, w.dgd, 4096, st.hd, kDRnn, G[W_DRNN_WHH], kDRnn, 0.f));
   if (G[W_DRNN_BIH] || G[W_DRNN_BHH]) {
     T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dgd, 4096, w.tmp, 4096, 0.f));
     if (G[W_DRNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_DRNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));

@@ -20,6 +20,8 @@ namespace t2 {
 int blas_handle(T2Model* m, cudaStream_t s, cublasHandle_t* out);
 int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
             float* C, long ldc, float beta);
+int gemm_rm_wgrad(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+                  float* C, long ldc, float beta);
 
 namespace {
 
@@ -306,7 +308,7 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
   if (G[L.wbase + 1]) T2_TRY(gemm_rm(bl, false, false, 1, L.cout, (int)Mp, ones, Mp, gz_p, L.cout, G[L.wbase + 1], L.cout, 0.f));      // d conv bias
   if (G[L.wbase]) {
     for (int k = 0; k < kConvK; ++k)
-      T2_TRY(gemm_rm(bl, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
+      T2_TRY(gemm_rm_wgrad(bl, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
                      dwpk + (long)k * L.cin, (long)kConvK * L.cin, 0.f));
     const long nw = (long)L.cout * L.cin * kConvK;
     unpack_conv_grad_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(dwpk, G[L.wbase], L.cout, L.cin, kConvK);
