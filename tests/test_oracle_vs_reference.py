@@ -36,3 +36,48 @@ def test_reference_state_dict_layout():
     assert list(sd.keys()) == list(want.keys())
     for k, v in sd.items():
         assert tuple(v.shape) == tuple(want[k]), k
+
+
+def test_reference_training_step_gradients_live():
+    """Full training step (forward + Tacotron2Loss + backward) of the unmodified reference vs torch autograd through
+    the oracle: every parameter gradient, full tensors (the committed fixtures tests/golden/grad_*.npz keep samples)."""
+    import importlib.util
+    from tests.test_oracle_golden import oracle_train_step
+    ref = import_reference_model()
+    spec = importlib.util.spec_from_file_location("ref_loss_function", "/root/reference/loss_function.py")
+    lf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lf)
+    B, T, Tm, seed = 3, 15, 8, 91
+    sd = synth_state_dict(4321, scale=2.0)
+    g = torch.Generator().manual_seed(seed)
+    text = rand_text(B, T, seed + 1)
+    tl = torch.sort(torch.randint(T // 3, T + 1, (B,), generator=g), descending=True)[0]
+    tl[0] = T
+    ol = torch.randint(Tm // 3, Tm + 1, (B,), generator=g)
+    ol[1] = Tm
+    mels = torch.randn(B, 80, Tm, generator=g)
+    gt = torch.zeros(B, Tm)
+    for i, n in enumerate(ol.tolist()):
+        mels[i, :, n:] = 0.0
+        gt[i, n - 1:] = 1.0
+    m = dict(pk=keep_mask((Tm + 1, 2, B, 256), 0.5, seed + 2), ak=keep_mask((Tm, B, 1024), 0.1, seed + 3),
+             dk=keep_mask((Tm, B, 1024), 0.1, seed + 4), ek=keep_mask((3, B, 512, T), 0.5, seed + 5),
+             qk4=keep_mask((4, B, 512, Tm), 0.5, seed + 6), qk1=keep_mask((B, 80, Tm), 0.5, seed + 7))
+    model = ref.Tacotron2(default_hparams())
+    model.load_state_dict(sd)
+    model.train()
+    masks = [m["ek"][i].bool() for i in range(3)] + [m["pk"][:, 0].bool(), m["pk"][:, 1].bool()]
+    for t in range(Tm):
+        masks += [m["ak"][t].bool(), m["dk"][t].bool()]
+    masks += [m["qk4"][i].bool() for i in range(4)] + [m["qk1"].bool()]
+    with injected_dropout(ref, MaskInjector(masks)):
+        out = model((text, tl, mels, int(tl.max()), ol))
+    loss = lf.Tacotron2Loss()(out, (mels, gt))
+    loss.backward()
+    o_loss, _, o_grads = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
+    assert abs(float(loss) - float(o_loss)) < 1e-5 * abs(float(loss))
+    for k, p in model.named_parameters():
+        if float(p.grad.abs().max()) < 1e-5:      # conv biases in front of a training-mode BatchNorm: rounding noise
+            assert float(o_grads[k].abs().max()) < 1e-4
+            continue
+        assert rel_err(o_grads[k], p.grad) < 1e-4, k
