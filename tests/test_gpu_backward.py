@@ -155,3 +155,38 @@ def test_postnet_and_encoder_modules_backward_vs_oracle(B, T):
     print("encoder/postnet backward B=%d T=%d: worst %.2e" % (B, T, max(errs.values())))
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad
+
+
+def test_full_size_backward_tensor_core_vs_simt_gemms_and_determinism(monkeypatch):
+    """B=64, T_enc=150 (the benchmark shape), 24 teacher-forced steps, Philox dropout: the gradients with the reverse
+    recurrence's GEMMs on the tcgen05 engine agree with the fp32 SIMT kernels, and two runs are bit-identical."""
+    torch.manual_seed(7)
+    model = t2.Tacotron2(t2.create_hparams()).cuda().train()
+    dec = model.decoder
+    B, Te, T = 64, 150, 24
+    g = torch.Generator().manual_seed(3)
+    memory = torch.randn(B, Te, 512, generator=g).cuda()
+    mels = torch.randn(B, 80, T, generator=g).cuda()
+    lens = torch.sort(torch.randint(75, Te + 1, (B,), generator=g), descending=True)[0]
+    lens[0] = Te
+    d_mel = torch.randn(B, 80, T, generator=g).cuda()
+    d_gate = torch.randn(B, T, generator=g).cuda()
+    pk = keep_mask((T + 1, 2, B, 256), 0.5, 1)
+    ak, dk = keep_mask((T, B, 1024), 0.1, 2), keep_mask((T, B, 1024), 0.1, 3)
+
+    def run(mode):
+        monkeypatch.setenv("T2_BWD_GEMM", mode)
+        for p in dec.parameters():
+            p.grad = None
+        mem = memory.clone().requires_grad_(True)
+        with t2.dropout_masks(prenet=pk, att=ak, dec=dk):
+            mel, gate, _ = dec(mem, mels, lens.cuda())
+            ((mel * d_mel).sum() + (gate * d_gate).sum()).backward()
+        torch.cuda.synchronize()
+        return [mem.grad.clone()] + [p.grad.clone() for p in dec.parameters()]
+
+    a, b, c = run("tc"), run("tc"), run("simt")
+    assert all(torch.equal(x, y) for x, y in zip(a, b)), "backward is not deterministic"
+    worst = max(rel_err(x, y) for x, y in zip(a, c))
+    print("full-size backward: tcgen05 vs SIMT GEMMs worst rel diff %.2e" % worst)
+    assert worst < 1e-4
