@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   float* s_bias_p = reinterpret_cast<float*>(sp); sp += 8 * 4;                // bias of this CTA's 8 projection columns
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
-  float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128]
+  float* s_e = reinterpret_cast<float*>(sp); sp += ntiles * 128 * 4;          // [ntiles * 128] attention weights
+  float* s_ep = reinterpret_cast<float*>(sp);                                 // [4][ntiles * 128] energy partial sums: one writer
+                                                                              // per (column group, position), summed in a fixed
+                                                                              // order -> bit-reproducible (no shared-memory atomics)
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
@@ -721,7 +724,6 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     };
     grid_arrive(ctrl, bar_target);                                             // B2 (arrive): q written
     if (att_cta) {
-      for (int i = tid; i < ntiles * 128; i += kThreads) s_e[i] = 0.f;
       att_im2col_mma(0, min(2, ntiles));
       if (smem_rows > 64) stage_memory_rows(64, smem_rows);   // ring space beyond the 2-tile A image
     }
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
               if (c >= nact * 16) break;
               const int tile = c >> 4, col0 = (c & 15) * 8;
               if (tile != cur_tile) {
-                if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+                if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) s_ep[cg * ntiles * 128 + jp] = part; }
                 part = 0.f; cur_tile = tile;
               }
               const int j = (t0 + tile) * 128 + quad * 32 + lane;
@@ -781,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
               }
             }
           }
-          if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) atomicAdd(&s_e[jp], part); }
+          if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) s_ep[cg * ntiles * 128 + jp] = part; }
         }
         ptx::tc_fence_before();
         __syncthreads();
@@ -790,16 +792,17 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       // mask + softmax (model.py:79-82): every warp reduces all T energies itself (shuffles only, no
       // cross-warp exchange), then the threads split the normalised write-out
       const int len = p.mem_len ? p.mem_len[b] : T;
+      const int eN = ntiles * 128;
+      auto eraw = [&](int j) { return (s_ep[j] + s_ep[eN + j]) + (s_ep[2 * eN + j] + s_ep[3 * eN + j]); };
       float mx = -INFINITY;
-      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, (j < len) ? s_e[j] : p.score_mask_value);
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, (j < len) ? eraw(j) : p.score_mask_value);
       mx = warp_max_f(mx);
       float sum = 0.f;
-      for (int j = lane; j < T; j += 32) sum += expf(((j < len) ? s_e[j] : p.score_mask_value) - mx);
+      for (int j = lane; j < T; j += 32) sum += expf(((j < len) ? eraw(j) : p.score_mask_value) - mx);
       sum = warp_sum_f(sum);
       const float inv = 1.f / sum;
-      __syncthreads();                                           // all warps have read the raw energies
       for (int j = tid; j < T; j += kThreads) {
-        const float a = expf(((j < len) ? s_e[j] : p.score_mask_value) - mx) * inv;
+        const float a = expf(((j < len) ? eraw(j) : p.score_mask_value) - mx) * inv;
         s_e[j] = a;
         s_pad0[halfk + j] = a;                                                // becomes "previous"
         s_pad1[halfk + j] += a;                                               // model.py:365
@@ -999,7 +1002,7 @@ static size_t persistent_smem_bytes(int T) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
   return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
-         (size_t)kRows * kXchStride * 4 + kRows * 4 + 32 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)ntiles * 128 * 4 + 1024;
+         (size_t)kRows * kXchStride * 4 + kRows * 4 + 32 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)5 * ntiles * 128 * 4 + 1024;
 }
 
 size_t persistent_ws_bytes(int B, int T, int cap) {

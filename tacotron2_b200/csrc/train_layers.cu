@@ -232,16 +232,40 @@ __global__ void padded_to_rows_kernel(const float* __restrict__ gp, const float*
   if (add_rows) v += add_rows[i];
   out[i] = v;
 }
-// embedding gradient: one block per symbol, deterministic                                   model.py:503
-__global__ void embed_bwd_kernel(const int64_t* __restrict__ text, const float* __restrict__ gp, float* __restrict__ d_emb, int B, int T,
-                                 int n_symbols) {
-  const int sym = blockIdx.x;
-  for (int c = threadIdx.x; c < kEnc; c += blockDim.x) {
+// embedding gradient: one block per symbol; the block first lists the positions that hold its symbol (ascending, so the
+// summation order is fixed), then adds their gradient rows                                    model.py:503
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ text, const float* __restrict__ gp,
+                                                        float* __restrict__ d_emb, int B, int T, int n_symbols) {
+  extern __shared__ int s_rows[];                      // (B * T) matching positions, compacted
+  __shared__ int s_cnt[256 + 1];
+  const int sym = blockIdx.x, tid = threadIdx.x;
+  const int M = B * T;
+  const int per = (M + 255) / 256;
+  const int r0 = tid * per, r1 = r0 + per < M ? r0 + per : M;
+  int cnt = 0;
+  for (int r = r0; r < r1; ++r) {
+    long v = text[r];
+    v = v < 0 ? 0 : (v >= n_symbols ? n_symbols - 1 : v);
+    cnt += v == sym;
+  }
+  s_cnt[tid + 1] = cnt;
+  if (tid == 0) s_cnt[0] = 0;
+  __syncthreads();
+  if (tid == 0) for (int i = 1; i <= 256; ++i) s_cnt[i] += s_cnt[i - 1];
+  __syncthreads();
+  int o = s_cnt[tid];
+  for (int r = r0; r < r1; ++r) {
+    long v = text[r];
+    v = v < 0 ? 0 : (v >= n_symbols ? n_symbols - 1 : v);
+    if (v == sym) s_rows[o++] = r;
+  }
+  __syncthreads();
+  const int n = s_cnt[256];
+  for (int c = tid; c < kEnc; c += 256) {
     float s = 0.f;
-    for (long r = 0; r < (long)B * T; ++r) {
-      long v = text[r];
-      v = v < 0 ? 0 : (v >= n_symbols ? n_symbols - 1 : v);
-      if (v == sym) s += gp[d_prow((int)(r / T), (int)(r % T), T) * kEnc + c];
+    for (int i = 0; i < n; ++i) {
+      const int r = s_rows[i];
+      s += gp[d_prow(r / T, r % T, T) * kEnc + c];
     }
     d_emb[(long)sym * kEnc + c] = s;
   }
@@ -664,7 +688,9 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
     T2_LAUNCH_CHECK();
   }
   if (a->text && G[W_EMB]) {
-    embed_bwd_kernel<<<m->cfg.n_symbols, 128, 0, s>>>(a->text, g, G[W_EMB], B, T, m->cfg.n_symbols);
+    if ((size_t)B * T * sizeof(int) > 200 * 1024) return fail(T2_ERR_UNSUPPORTED, "encoder backward: B * T too large for the embedding kernel");
+    T2_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)B * T * sizeof(int))));
+    embed_bwd_kernel<<<m->cfg.n_symbols, 256, (size_t)B * T * sizeof(int), s>>>(a->text, g, G[W_EMB], B, T, m->cfg.n_symbols);
     T2_LAUNCH_CHECK();
   }
   return T2_OK;

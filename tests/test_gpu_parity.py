@@ -172,3 +172,22 @@ def test_philox_mode_is_deterministic_and_statistically_sane():
         with torch.no_grad():
             res.append(model.inference(text)[0].cpu())
     assert rel_err(res[0], res[1]) < TOL
+
+
+def test_persistent_decoder_is_bit_reproducible():
+    """Two runs with the same inputs and masks give bit-identical mel / gate / alignments at the benchmark shape (the
+    attention energies are summed in a fixed order: no shared-memory atomics) -- stop decisions cannot flip run to run."""
+    torch.manual_seed(11)
+    model = t2.Tacotron2(t2.create_hparams()).cuda().eval()
+    model._t2_engine().impl = _capi.IMPL_PERSISTENT
+    model.decoder.max_decoder_steps = 20
+    model.decoder.gate_threshold = 1.0
+    g = torch.Generator().manual_seed(3)
+    memory = torch.randn(64, 150, 512, generator=g).cuda()
+    keep = keep_mask((20, 2, 64, 256), 0.5, 9)
+    outs = []
+    for _ in range(3):
+        with torch.no_grad(), t2.dropout_masks(prenet=keep):
+            outs.append([x.clone() for x in model.decoder.inference(memory)])
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
