@@ -18,6 +18,7 @@
 #include "decoder.h"
 #include "gemm_f32.cuh"
 #include "umma.cuh"
+#include "wgrad_tc.h"
 
 namespace t2 {
 
@@ -577,6 +578,7 @@ struct BwdWs {
   float *dga, *dgd, *q, *dq, *awc, *pm, *dpm, *dctx, *dy, *gs, *cols, *pb, *pe, *gdc, *gac, *cacc, *gcat, *dv, *ones, *weff,
       *dweff, *tmp, *gproj, *weffT, *inv_scale;
   uint8_t *img_d, *img_a; DecoderCtrl* ctrl;
+  void* wg; size_t wg_bytes;
 };
 size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   uintptr_t p = (uintptr_t)base;
@@ -603,6 +605,8 @@ size_t carve(char* base, int B, int Te, int T, BwdWs* w) {
   d.img_d = (uint8_t*)(((uintptr_t)d.img_d + 1023) & ~(uintptr_t)1023);
   d.img_a = (uint8_t*)(((uintptr_t)d.img_a + 1023) & ~(uintptr_t)1023);
   d.ctrl = (DecoderCtrl*)take(sizeof(DecoderCtrl) / 4 + 64);
+  d.wg_bytes = wgrad_tc_ws_bytes(B, T);
+  d.wg = take(d.wg_bytes / 4 + 64);
   if (w) *w = d;
   return (size_t)(p - (uintptr_t)base);
 }
@@ -768,25 +772,35 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
   float* const* G = a->grads;
   const float* x2 = a->teacher_prenet;
   const int TBi = (int)TB;
+  // LSTM weight / bias gradients: our tcgen05 split-fp16 engine (default) or plain cuBLAS fp32 GEMMs (T2_WGRAD=cublas)
+  bool tc_wgrad = true;
+  {
+    const char* e = getenv("T2_WGRAD");
+    if (e && e[0] == 'c') tc_wgrad = false;
+  }
+  if (tc_wgrad) {
+    T2_TRY(wgrad_tc_run(m, B, T, w.dga, w.dgd, x2, st, G, w.wg, w.wg_bytes, s));
+  } else {
   if (G[W_ARNN_WIH]) {   // [x2_t | ctx_{t-1}]                                             model.py:352
-    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kPre, TBi, w.dga, 4096, x2, kPre, G[W_ARNN_WIH], kPre + kEnc, 0.f));
-    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dga, 4096, st.ctx, kEnc, G[W_ARNN_WIH] + kPre, kPre + kEnc, 0.f));
-  }
-  if (G[W_ARNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dga, 4096, st.ha, kARnn, G[W_ARNN_WHH], kARnn, 0.f));
-  if (G[W_ARNN_BIH] || G[W_ARNN_BHH]) {
-    T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dga, 4096, w.tmp, 4096, 0.f));
-    if (G[W_ARNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
-    if (G[W_ARNN_BHH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BHH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
-  }
-  if (G[W_DRNN_WIH]) {   // [ah_t | ctx_t]                                                 model.py:366-367
-    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dgd, 4096, st.ha + (size_t)B * kARnn, kARnn, G[W_DRNN_WIH], kARnn + kEnc, 0.f));
-    T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dgd, 4096, st.ctx + (size_t)B * kEnc, kEnc, G[W_DRNN_WIH] + kARnn, kARnn + kEnc, 0.f));
-  }
-  if (G[W_DRNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kDRnn, TBi, w.dgd, 4096, st.hd, kDRnn, G[W_DRNN_WHH], kDRnn, 0.f));
-  if (G[W_DRNN_BIH] || G[W_DRNN_BHH]) {
-    T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dgd, 4096, w.tmp, 4096, 0.f));
-    if (G[W_DRNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_DRNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
-    if (G[W_DRNN_BHH]) T2_CUDA(cudaMemcpyAsync(G[W_DRNN_BHH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
+      T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kPre, TBi, w.dga, 4096, x2, kPre, G[W_ARNN_WIH], kPre + kEnc, 0.f));
+      T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dga, 4096, st.ctx, kEnc, G[W_ARNN_WIH] + kPre, kPre + kEnc, 0.f));
+    }
+    if (G[W_ARNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dga, 4096, st.ha, kARnn, G[W_ARNN_WHH], kARnn, 0.f));
+    if (G[W_ARNN_BIH] || G[W_ARNN_BHH]) {
+      T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dga, 4096, w.tmp, 4096, 0.f));
+      if (G[W_ARNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
+      if (G[W_ARNN_BHH]) T2_CUDA(cudaMemcpyAsync(G[W_ARNN_BHH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (G[W_DRNN_WIH]) {   // [ah_t | ctx_t]                                                 model.py:366-367
+      T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kARnn, TBi, w.dgd, 4096, st.ha + (size_t)B * kARnn, kARnn, G[W_DRNN_WIH], kARnn + kEnc, 0.f));
+      T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kEnc, TBi, w.dgd, 4096, st.ctx + (size_t)B * kEnc, kEnc, G[W_DRNN_WIH] + kARnn, kARnn + kEnc, 0.f));
+    }
+    if (G[W_DRNN_WHH]) T2_TRY(gemm_rm_wgrad(bl, true, false, 4096, kDRnn, TBi, w.dgd, 4096, st.hd, kDRnn, G[W_DRNN_WHH], kDRnn, 0.f));
+    if (G[W_DRNN_BIH] || G[W_DRNN_BHH]) {
+      T2_TRY(gemm_rm(bl, false, false, 1, 4096, TBi, w.ones, TBi, w.dgd, 4096, w.tmp, 4096, 0.f));
+      if (G[W_DRNN_BIH]) T2_CUDA(cudaMemcpyAsync(G[W_DRNN_BIH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
+      if (G[W_DRNN_BHH]) T2_CUDA(cudaMemcpyAsync(G[W_DRNN_BHH], w.tmp, 4096 * 4, cudaMemcpyDeviceToDevice, s));
+    }
   }
   // projection + gate on [dh_t | ctx_t]                                                   model.py:373-378
   if (G[W_PROJ_W]) {

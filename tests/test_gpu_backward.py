@@ -50,8 +50,10 @@ def oracle_decoder_grads(sd, memory, mels, lens, pk, ak, dk, d_mel, d_gate, d_al
 @pytest.mark.parametrize("B,Te,T,training,use_align", [(3, 19, 7, True, False), (5, 40, 12, True, True),
                                                        (4, 150, 9, False, False), (64, 33, 5, True, False)])
 def test_decoder_backward_vs_oracle_autograd(B, Te, T, training, use_align, gemm, monkeypatch):
-    """gemm: the reverse recurrence's skinny GEMMs on the tcgen05 split-fp16 engine (default) or the fp32 SIMT kernel."""
+    """gemm = tc: the reverse recurrence's skinny GEMMs and the time-batched LSTM weight gradients on the tcgen05
+    split-fp16 engines (default); simt: fp32 SIMT kernels / plain cuBLAS fp32 GEMMs (cross-check)."""
     monkeypatch.setenv("T2_BWD_GEMM", gemm)
+    monkeypatch.setenv("T2_WGRAD", "tc" if gemm == "tc" else "cublas")
     sd = synth_state_dict(seed=21, scale=2.0)
     memory, mels, lens, pk, ak, dk, d_mel, d_gate, d_align = decoder_case(B, Te, T, seed=100 + B)
     if not use_align:
@@ -176,6 +178,7 @@ def test_full_size_backward_tensor_core_vs_simt_gemms_and_determinism(monkeypatc
 
     def run(mode):
         monkeypatch.setenv("T2_BWD_GEMM", mode)
+        monkeypatch.setenv("T2_WGRAD", "tc" if mode == "tc" else "cublas")
         for p in dec.parameters():
             p.grad = None
         mem = memory.clone().requires_grad_(True)
