@@ -120,7 +120,8 @@ def test_encoder_and_postnet_modules_vs_oracle(B, T, conv_impl, monkeypatch):
 @pytest.mark.parametrize("impl,impl_name", IMPLS)
 def test_fresh_inputs_vs_oracle_edge_shapes(impl, impl_name):
     """Ragged / minimal shapes: B=1 T_text=1, odd T_text, B not a multiple of anything."""
-    for (B, T, S, seed) in [(1, 1, 5, 1), (7, 13, 9, 2), (2, 150, 6, 3), (70, 11, 4, 4), (3, 300, 3, 5)]:
+    for (B, T, S, seed) in [(1, 1, 5, 1), (7, 13, 9, 2), (2, 150, 6, 3), (70, 11, 4, 4), (3, 300, 3, 5), (2, 270, 3, 6),
+                            (2, 129, 4, 7), (2, 160, 3, 8)]:
         sd = synth_state_dict(100 + seed, gate_bias=-10.0, scale=2.0)
         model = make_model(sd, S, impl)
         text = rand_text(B, T, seed)
