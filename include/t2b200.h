@@ -240,6 +240,22 @@ size_t t2_postnet_stash_bytes(const T2Model* m, int32_t B, int32_t T);
 size_t t2_postnet_backward_workspace_bytes(const T2Model* m, int32_t B, int32_t T);
 int    t2_postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, void* stream);
 
+/* ---- Fused gradient clipping + Adam (train.py:229-236: clip_grad_norm_ then torch.optim.Adam.step) -----------
+ * n tensors (host arrays of device pointers + element counts).  grad_norm (device, 1 float) receives the total
+ * gradient norm BEFORE clipping; the gradients are scaled in place by min(1, max_norm / (norm + 1e-6)) like
+ * torch.nn.utils.clip_grad_norm_ (max_norm <= 0: no clipping), then exp_avg / exp_avg_sq / the parameters are updated
+ * exactly like torch.optim.Adam (L2 weight decay, bias correction with `step` counted from 1). */
+typedef struct T2AdamArgs {
+  int32_t n;
+  float* const* params; float* const* grads; float* const* exp_avg; float* const* exp_avg_sq; const int64_t* numel;
+  double lr, beta1, beta2, eps, weight_decay, max_norm;   /* doubles: 1 - beta2^step must not be rounded through fp32 */
+  int32_t step;
+  float* grad_norm;
+  void* ws; size_t ws_bytes;
+} T2AdamArgs;
+size_t t2_clip_adam_workspace_bytes(int64_t total_elements, int32_t n_tensors);
+int    t2_clip_adam_step(const T2AdamArgs* a, void* stream);
+
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
  * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on

@@ -4,5 +4,7 @@ from ._engine import dropout_masks  # noqa: F401
 from .hparams import create_hparams  # noqa: F401
 from .loss_function import Tacotron2Loss  # noqa: F401
 from .model import Decoder, Encoder, Postnet, Tacotron2  # noqa: F401
+from .optim import FusedClipAdam  # noqa: F401
 
-__all__ = ["Tacotron2", "Encoder", "Decoder", "Postnet", "Tacotron2Loss", "create_hparams", "dropout_masks"]
+__all__ = ["Tacotron2", "Encoder", "Decoder", "Postnet", "Tacotron2Loss", "create_hparams", "dropout_masks",
+           "FusedClipAdam"]

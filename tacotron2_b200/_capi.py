@@ -21,6 +21,7 @@ EXPORTS = [
     "t2_prenet_backward_workspace_bytes", "t2_prenet_backward",
     "t2_encoder_stash_bytes", "t2_encoder_backward_workspace_bytes", "t2_encoder_backward",
     "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
+    "t2_clip_adam_workspace_bytes", "t2_clip_adam_step",
 ]
 
 
@@ -79,6 +80,14 @@ class T2PrenetBwdArgs(C.Structure):
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class T2AdamArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("params", C.POINTER(C.c_void_p)), ("grads", C.POINTER(C.c_void_p)),
+                ("exp_avg", C.POINTER(C.c_void_p)), ("exp_avg_sq", C.POINTER(C.c_void_p)), ("numel", C.POINTER(C.c_int64)),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("max_norm", C.c_double), ("step", C.c_int32),
+                ("grad_norm", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
@@ -127,6 +136,9 @@ def lib():
     L.t2_encoder_forward.argtypes = [C.c_void_p, C.POINTER(T2EncoderArgs), C.c_void_p]
     L.t2_decoder_run.argtypes = [C.c_void_p, C.POINTER(T2DecoderArgs), C.c_void_p]
     L.t2_postnet_forward.argtypes = [C.c_void_p, C.POINTER(T2PostnetArgs), C.c_void_p]
+    L.t2_clip_adam_workspace_bytes.restype = C.c_size_t
+    L.t2_clip_adam_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.t2_clip_adam_step.argtypes = [C.POINTER(T2AdamArgs), C.c_void_p]
     L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
     L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]

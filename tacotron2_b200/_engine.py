@@ -71,6 +71,15 @@ def current_masks():
     return getattr(_tls, "masks", None) or dict(prenet=None, att=None, dec=None, enc=None, post=None)
 
 
+# Bumped by code that updates parameters in place without going through torch (the fused optimizer): part of the
+# handle-cache key, so the packed device-side copies are rebuilt.
+_weights_generation = [0]
+
+
+def bump_weights_generation():
+    _weights_generation[0] += 1
+
+
 _seed_counter = [0]
 
 
@@ -114,8 +123,8 @@ class Engine:
         if dev is None:
             raise RuntimeError("tacotron2_b200: the model must live on a CUDA device (B200); there is no "
                                "CPU path -- call .cuda() first")
-        key = tuple((named[n].data_ptr(), named[n]._version, named[n].dtype) if n in named else None
-                    for n, _ in self.spec)
+        key = (_weights_generation[0],) + tuple(
+            (named[n].data_ptr(), named[n]._version, named[n].dtype) if n in named else None for n, _ in self.spec)
         if self.handle is not None and key == self.key and dev == self.device:
             return
         L = _capi.lib()

@@ -108,6 +108,8 @@ def test_ctypes_structs_match_c_layout(tmp_path):
                              "dec_keep", "seed", "score_mask_value", "align", "stash", "stash_bytes", "d_mel", "d_gate",
                              "d_align", "d_memory", "d_prenet", "grads", "n_grads", "ws", "ws_bytes"],
         "T2PrenetBwdArgs": ["frames", "M", "keep", "seed", "d_out", "grads", "n_grads", "ws", "ws_bytes"],
+        "T2AdamArgs": ["n", "params", "grads", "exp_avg", "exp_avg_sq", "numel", "lr", "beta1", "beta2", "eps", "weight_decay",
+                       "max_norm", "step", "grad_norm", "ws", "ws_bytes"],
         "T2PostnetArgs": ["mel", "mel_batch_stride", "lengths", "B", "T", "training", "keep", "seed",
                           "add_residual", "mel_post", "ws", "ws_bytes", "stash", "stash_bytes"],
     }

@@ -195,3 +195,43 @@ def test_full_size_backward_tensor_core_vs_simt_gemms_and_determinism(monkeypatc
     worst = max(rel_err(x, y) for x, y in zip(a, c))
     print("full-size backward: tcgen05 vs SIMT GEMMs worst rel diff %.2e" % worst)
     assert worst < 1e-4
+
+
+def test_fused_clip_adam_matches_torch():
+    """t2.FusedClipAdam.step(max_norm) == clip_grad_norm_ + torch.optim.Adam.step (train.py:229-236), 4 steps, odd sizes,
+    clipping active in some steps and not in others; the engine notices the in-place parameter update."""
+    g = torch.Generator().manual_seed(5)
+    shapes = [(7,), (129, 3), (4096, 33), (1,), (65537,), (80, 512, 5)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-6)
+    our_opt = t2.FusedClipAdam(our_p, lr=1e-3, weight_decay=1e-6)
+    for it in range(4):
+        scale = [5.0, 1e-3, 0.3, 50.0][it]
+        for a, b in zip(ref_p, our_p):
+            gr = torch.randn(a.shape, generator=g).cuda() * scale
+            a.grad, b.grad = gr.clone(), gr.clone()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        ref_opt.step()
+        n_our = our_opt.step(max_norm=1.0)
+        assert abs(float(n_ref) - float(n_our)) < 1e-5 * float(n_ref)
+        for a, b in zip(ref_p, our_p):
+            assert rel_err(b, a) < 2e-6 and rel_err(b.grad, a.grad) < 2e-6
+    sd_ref, sd_our = ref_opt.state_dict(), our_opt.state_dict()
+    for k in sd_ref["state"]:
+        assert rel_err(sd_our["state"][k]["exp_avg"], sd_ref["state"][k]["exp_avg"]) < 2e-6
+        assert rel_err(sd_our["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"]) < 2e-6
+        assert float(sd_our["state"][k]["step"]) == float(sd_ref["state"][k]["step"])
+    # in-place update through the library -> the next forward uses the new weights
+    model = t2.Tacotron2(t2.create_hparams()).cuda().eval()
+    opt = t2.FusedClipAdam(model.parameters(), lr=1e-2)
+    text = torch.randint(0, 148, (2, 9)).cuda()
+    model.decoder.max_decoder_steps = 4
+    with torch.no_grad():
+        before = model.inference(text)[0].clone()
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    with torch.no_grad():
+        after = model.inference(text)[0]
+    assert not torch.equal(before, after)

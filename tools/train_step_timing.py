@@ -16,7 +16,8 @@ iters = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 torch.manual_seed(1234)
 hp = t2.create_hparams()
 model = t2.Tacotron2(hp).cuda().train()
-opt = torch.optim.Adam(model.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+fused = os.environ.get("T2_TORCH_ADAM") is None
+opt = (t2.FusedClipAdam if fused else torch.optim.Adam)(model.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
 crit = t2.Tacotron2Loss()
 g = torch.Generator().manual_seed(0)
 text = torch.randint(0, 148, (B, Tt), generator=g).cuda()
@@ -40,8 +41,11 @@ for it in range(iters):
     ev[1].record()
     loss.backward()
     ev[2].record()
-    gn = torch.nn.utils.clip_grad_norm_(model.parameters(), hp.grad_clip_thresh)
-    opt.step()
+    if fused:
+        gn = opt.step(max_norm=hp.grad_clip_thresh)
+    else:
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), hp.grad_clip_thresh)
+        opt.step()
     ev[3].record()
     torch.cuda.synchronize()
     fw, bw, up = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
