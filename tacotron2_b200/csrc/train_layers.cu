@@ -14,6 +14,7 @@
 #include "decoder.h"
 #include "gemm_f32.cuh"
 #include "train_layers.h"
+#include "wgrad_tc.h"
 
 namespace t2 {
 
@@ -279,6 +280,75 @@ struct ConvLayer {
   uint32_t site; const uint8_t* keep;
 };
 
+// ---- conv weight gradient on the tcgen05 engine (wgrad_tc.cu) ---------------------------------------------------------
+// dW_k[co][ci] = sum_r G_z[r][co] X[r + k - 2][ci]: K = padded rows in chunks of 64, A = G_z^T images (per-channel power-of-two
+// scale), B = X^T images, one set per tap (source rows shifted by k - 2), 128 x 256 tiles, K splits reduced in a fixed order.
+struct WgConvWs { uint8_t* img_a; uint8_t* img_b; float* part; float* stat; float* scale; float* inv; float* colsum; WgJob* jobs; };
+size_t wgconv_bytes(int B, int T, WgConvWs* w, char* base) {
+  const long Mp = (long)B * (T + 2 * kPadRows);
+  const long nch = (Mp + 63) / 64;
+  const int seg = wgrad_seg((int)nch), nsplit = (int)((nch + seg - 1) / seg);
+  uintptr_t p = (uintptr_t)base;
+  auto take = [&](size_t n) { uintptr_t r = p; p += (n + 1023) & ~(size_t)1023; return r; };
+  WgConvWs d;
+  d.img_a = (uint8_t*)take((size_t)nch * 4 * kWgTileA);                 // cout <= 512: 4 tiles of 128 rows
+  d.img_b = (uint8_t*)take((size_t)kConvK * nch * 2 * kWgTileB);        // cin <= 512: 2 tiles of 256 rows, 5 taps
+  d.part = (float*)take((size_t)nsplit * 512 * (kConvK * 512) * 4);
+  d.stat = (float*)take(wg_colstats_ws_bytes(512));
+  d.scale = (float*)take(512 * 4); d.inv = (float*)take(512 * 4); d.colsum = (float*)take(512 * 4);
+  d.jobs = (WgJob*)take((size_t)2048 * sizeof(WgJob));
+  if (w) *w = d;
+  return (size_t)(p - (uintptr_t)base) + 1024;
+}
+__global__ void wgconv_reduce_kernel(const float* __restrict__ part, int nsplit, int coutP, int ldp, int cinP, int cout, int cin,
+                                     float* __restrict__ dW) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // dW (co, ci, k) state_dict layout
+  if (i >= (long)cout * cin * kConvK) return;
+  const int k = (int)(i % kConvK); const long r = i / kConvK; const int ci = (int)(r % cin); const int co = (int)(r / cin);
+  float s = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) s += part[((long)sp * coutP + co) * ldp + (long)k * cinP + ci];
+  dW[i] = s;
+}
+int conv_wgrad_tc(const ConvLayer& L, int B, int T, const float* gz_p, const float* xp, float* dW, float* d_cbias, const WgConvWs& w,
+                  cudaStream_t s) {
+  const long Mp = (long)B * (T + 2 * kPadRows);
+  const int nch = (int)((Mp + 63) / 64);
+  const int seg = wgrad_seg(nch), nsplit = (nch + seg - 1) / seg;
+  const int ntA = (L.cout + 127) / 128, ntB = (L.cin + 255) / 256;
+  const int coutP = ntA * 128, cinP = ntB * 256, ldp = kConvK * cinP;
+  fill1_kernel<<<2, 256, 0, s>>>(w.inv, 1.f, 512);
+  T2_LAUNCH_CHECK();
+  T2_TRY(wg_colstats(gz_p, Mp, L.cout, w.stat, w.scale, w.inv, w.colsum, s));
+  if (d_cbias) T2_CUDA(cudaMemcpyAsync(d_cbias, w.colsum, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, s));
+  if (!dW) return T2_OK;
+  T2_TRY(wg_transpose_images(gz_p, L.cout, 0, Mp, 64, nch, L.cout, 128, w.scale, w.img_a, s));
+  const size_t b_img = (size_t)nch * ntB * kWgTileB;
+  for (int k = 0; k < kConvK; ++k)
+    T2_TRY(wg_transpose_images(xp, L.cin, k - kPadRows, Mp, 64, nch, L.cin, 256, nullptr, w.img_b + (size_t)k * b_img, s));
+  std::vector<WgJob> jobs;
+  for (int k = 0; k < kConvK; ++k)
+    for (int ia = 0; ia < ntA; ++ia)
+      for (int jb = 0; jb < ntB; ++jb)
+        for (int sp = 0; sp < nsplit; ++sp) {
+          WgJob j;
+          const int c0 = sp * seg, n = (nch - c0) < seg ? (nch - c0) : seg;
+          j.a_stride = (uint32_t)ntA * kWgTileA; j.b_stride = (uint32_t)ntB * kWgTileB;
+          j.a = w.img_a + (size_t)c0 * j.a_stride + (size_t)ia * kWgTileA;
+          j.b = w.img_b + (size_t)k * b_img + (size_t)c0 * j.b_stride + (size_t)jb * kWgTileB;
+          j.nchunks = n;
+          j.out = w.part + ((size_t)sp * coutP + (size_t)ia * 128) * ldp + (size_t)k * cinP + (size_t)jb * 256;
+          j.ldo = ldp;
+          j.inv_scale = w.inv + ia * 128;
+          jobs.push_back(j);
+        }
+  if (jobs.size() > 2048) return fail(T2_ERR_UNSUPPORTED, "conv wgrad: too many jobs");
+  T2_TRY(wg_run_jobs(jobs, w.jobs, s));
+  const long n = (long)L.cout * L.cin * kConvK;
+  wgconv_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.part, nsplit, coutP, ldp, cinP, L.cout, L.cin, dW);
+  T2_LAUNCH_CHECK();
+  return T2_OK;
+}
+
 int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* xp, float* zp,
              float* stats, float* yp, float* y_plain, bool update_running, float* partial, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
@@ -313,7 +383,7 @@ int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
 // non-null, and the gradients of conv.weight / conv.bias / bn.weight / bn.bias.
 int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* g, int g_padded,
              const float* xp, const float* zp, const float* stats, const float* yp, float* gz_p, float* gx_p, float* sums, float* dwpk,
-             const float* ones, float* const* G, cudaStream_t s) {
+             const float* ones, float* const* G, const WgConvWs* wg, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
   float* partial = sums + 2 * L.cout;      // (kRedSplit, 2, cout) scratch behind the two result rows
@@ -329,14 +399,18 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
   T2_LAUNCH_CHECK();
   if (G[L.wbase + 3]) T2_CUDA(cudaMemcpyAsync(G[L.wbase + 3], sums, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, s));           // d beta
   if (G[L.wbase + 2]) T2_CUDA(cudaMemcpyAsync(G[L.wbase + 2], sums + L.cout, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, s));  // d gamma
-  if (G[L.wbase + 1]) T2_TRY(gemm_rm(bl, false, false, 1, L.cout, (int)Mp, ones, Mp, gz_p, L.cout, G[L.wbase + 1], L.cout, 0.f));      // d conv bias
-  if (G[L.wbase]) {
-    for (int k = 0; k < kConvK; ++k)
-      T2_TRY(gemm_rm_wgrad(bl, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
-                     dwpk + (long)k * L.cin, (long)kConvK * L.cin, 0.f));
-    const long nw = (long)L.cout * L.cin * kConvK;
-    unpack_conv_grad_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(dwpk, G[L.wbase], L.cout, L.cin, kConvK);
-    T2_LAUNCH_CHECK();
+  if (wg) {   // weight + bias gradient on our tcgen05 engine
+    T2_TRY(conv_wgrad_tc(L, B, T, gz_p, xp, G[L.wbase], G[L.wbase + 1], *wg, s));
+  } else {
+    if (G[L.wbase + 1]) T2_TRY(gemm_rm(bl, false, false, 1, L.cout, (int)Mp, ones, Mp, gz_p, L.cout, G[L.wbase + 1], L.cout, 0.f));      // d conv bias
+    if (G[L.wbase]) {
+      for (int k = 0; k < kConvK; ++k)
+        T2_TRY(gemm_rm_wgrad(bl, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
+                       dwpk + (long)k * L.cin, (long)kConvK * L.cin, 0.f));
+      const long nw = (long)L.cout * L.cin * kConvK;
+      unpack_conv_grad_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(dwpk, G[L.wbase], L.cout, L.cin, kConvK);
+      T2_LAUNCH_CHECK();
+    }
   }
   if (gx_p) {
     for (int k = 0; k < kConvK; ++k)
@@ -517,7 +591,7 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
 size_t postnet_backward_ws_bytes(int B, int T) {
   const size_t Mp = (size_t)B * (T + 2 * kPadRows);
   return 3 * a256(Mp * kPost * 4) + a256((size_t)B * T * kMel * 4) + a256(Mp * 4) + a256((size_t)kPost * kPost * kConvK * 4) +
-         a256((size_t)(2 + 2 * kRedSplit) * kPost * 4) + 1024;
+         a256((size_t)(2 + 2 * kRedSplit) * kPost * 4) + wgconv_bytes(B, T, nullptr, nullptr) + 4096;
 }
 
 int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
@@ -535,7 +609,12 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
   float* grow = (float*)p; p += a256((size_t)B * T * kMel * 4);
   float* ones = (float*)p; p += a256(Mp * 4);
   float* dwpk = (float*)p; p += a256((size_t)kPost * kPost * kConvK * 4);
-  float* sums = (float*)p;
+  float* sums = (float*)p; p += a256((size_t)(2 + 2 * kRedSplit) * kPost * 4);
+  WgConvWs wgws; const WgConvWs* wg = nullptr;
+  {
+    const char* e = getenv("T2_WGRAD");
+    if (!(e && e[0] == 'c')) { wgconv_bytes(B, T, &wgws, (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023)); wg = &wgws; }
+  }
   cublasHandle_t bl;
   T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)Mp);
@@ -553,7 +632,7 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
       T2_LAUNCH_CHECK();
     }
     T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.x[i], st.z[i], st.stats[i], st.x[i + 1], gz, gx, sums, dwpk,
-                    ones, a->grads, s));
+                    ones, a->grads, wg, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;
   }
@@ -612,7 +691,8 @@ size_t encoder_backward_ws_bytes(int B, int T) {
   constexpr int nsplit = 8;
   return a256((size_t)B * T * 8 * kEncH * 4) + a256((size_t)B * T * kEnc * 4) * 2 + a256((size_t)2 * nsplit * 64 * kEncH * 4) +
          a256((size_t)2 * 64 * kEncH * 4) + 3 * a256(Mp * kEnc * 4) + a256((Mp > (size_t)B * T ? Mp : (size_t)B * T) * 4) +
-         a256((size_t)kEnc * kEnc * kConvK * 4) + a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4) + a256(8 * kEncH * 4) + 2048;
+         a256((size_t)kEnc * kEnc * kConvK * 4) + a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4) + a256(8 * kEncH * 4) +
+         wgconv_bytes(B, T, nullptr, nullptr) + 4096;
 }
 
 int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
@@ -638,7 +718,12 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   float* ones = (float*)p; p += a256(n_ones * 4);
   float* dwpk = (float*)p; p += a256((size_t)kEnc * kEnc * kConvK * 4);
   float* sums = (float*)p; p += a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4);
-  float* tmp = (float*)p;
+  float* tmp = (float*)p; p += a256(8 * kEncH * 4);
+  WgConvWs wgws; const WgConvWs* wg = nullptr;
+  {
+    const char* e = getenv("T2_WGRAD");
+    if (!(e && e[0] == 'c')) { wgconv_bytes(B, T, &wgws, (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023)); wg = &wgws; }
+  }
   cublasHandle_t bl;
   T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((n_ones + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)n_ones);
@@ -679,7 +764,7 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   for (int i = 2; i >= 0; --i) {
     const bool need_gx = i > 0 || a->d_embedded || (a->text && G[W_EMB]);
     T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], gz,
-                    need_gx ? gx : nullptr, sums, dwpk, ones, G, s));
+                    need_gx ? gx : nullptr, sums, dwpk, ones, G, wg, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;
   }

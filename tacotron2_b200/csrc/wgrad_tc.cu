@@ -36,14 +36,14 @@ __global__ void __launch_bounds__(256) wg_colstats_kernel(const float* __restric
   const long per = (rows + kStatSplit - 1) / kStatSplit;
   const long r0 = blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
   float mx = 0.f, sm = 0.f;
-  for (long r = r0 + rg; r < r1; r += 8) {
+  if (c < C) for (long r = r0 + rg; r < r1; r += 8) {
     const float v = x[r * C + c];
     mx = fmaxf(mx, fabsf(v));
     sm += v;
   }
   rm[rg][cl] = mx; rs[rg][cl] = sm;
   __syncthreads();
-  if (rg == 0) {
+  if (rg == 0 && c < C) {
     for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, rm[i][cl]); sm += rs[i][cl]; }
     part[((long)blockIdx.y * 2 + 0) * C + c] = mx;
     part[((long)blockIdx.y * 2 + 1) * C + c] = sm;
@@ -66,20 +66,25 @@ __global__ void wg_colstats_finalize_kernel(const float* __restrict__ part, int 
 
 // ---- fp32 rows (chunk t = rows [t*B, t*B + B)) x C columns  ->  transposed operand images -----------------------
 // image of chunk t: C / TR tiles, each [hi plane TR x 128 B | lo plane], element (row = c % TR, k = b) = src[t*B+b][c] * scale[c]
-__global__ void __launch_bounds__(256) wg_transpose_img_kernel(const float* __restrict__ src, long ld, int B, int C, int TR,
-                                                               const float* __restrict__ scale, uint8_t* __restrict__ img) {
+__global__ void __launch_bounds__(256) wg_transpose_img_kernel(const float* __restrict__ src, long ld, long row0, long rows_total,
+                                                               int chunk_rows, int C, int TR, const float* __restrict__ scale,
+                                                               uint8_t* __restrict__ img) {
+  // chunk t = source rows [row0 + t * chunk_rows, + chunk_rows) (chunk_rows <= 64; the remaining k and rows outside
+  // [0, rows_total) are zero); columns >= C of the last tile are zero rows
   __shared__ float tile[64][65];
   const int c0 = blockIdx.x * 64, t = blockIdx.y, tid = threadIdx.x;
   for (int i = tid; i < 64 * 64; i += 256) {
     const int b = i >> 6, cc = i & 63;
-    tile[b][cc] = b < B ? src[((long)t * B + b) * ld + c0 + cc] : 0.f;
+    const long r = row0 + (long)t * chunk_rows + b;
+    tile[b][cc] = (b < chunk_rows && r >= 0 && r < rows_total && c0 + cc < C) ? src[r * ld + c0 + cc] : 0.f;
   }
   __syncthreads();
-  const int ntile = C / TR;
+  const int ntile = (C + TR - 1) / TR;
   for (int i = tid; i < 64 * 8; i += 256) {
     const int cc = i >> 3, k8 = i & 7;
     const int c = c0 + cc, r = c % TR, q = c / TR;
-    const float sc = scale ? scale[c] : 1.f;
+    if (q >= ntile) continue;
+    const float sc = (scale && c < C) ? scale[c] : 1.f;
     __align__(16) __half hh[8];
     __align__(16) __half ll[8];
 #pragma unroll
@@ -92,14 +97,6 @@ __global__ void __launch_bounds__(256) wg_transpose_img_kernel(const float* __re
 }
 
 // ---- the GEMM ----------------------------------------------------------------------------------------------
-struct WgJob {
-  const uint8_t* a; const uint8_t* b;     // first chunk of this job's A (gate) tile and B (feature) tile
-  uint32_t a_stride, b_stride;             // bytes between consecutive chunks
-  int32_t nchunks;
-  float* out; int32_t ldo;                 // partial tile (128 x 256) of this K split, row-major
-  const float* inv_scale;                  // (128) of the gate rows
-};
-
 __device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity) {
   const unsigned long long t0 = clock64();
   while (!ptx::mbar_try_wait(bar, parity)) {
@@ -237,16 +234,16 @@ int wgrad_tc_run(T2Model* m, int B, int T, const float* dga, const float* dgd, c
     T2_LAUNCH_CHECK();
     for (int k = 0; k < 2; ++k)
       if (G[bias_idx[l][k]]) T2_CUDA(cudaMemcpyAsync(G[bias_idx[l][k]], colsum, 4096 * 4, cudaMemcpyDeviceToDevice, s));
-    wg_transpose_img_kernel<<<dim3(4096 / 64, T), 256, 0, s>>>(dG[l], 4096, B, 4096, kTM, scale, img_a[l]);
+    wg_transpose_img_kernel<<<dim3(4096 / 64, T), 256, 0, s>>>(dG[l], 4096, 0, rows, B, 4096, kTM, scale, img_a[l]);
     T2_LAUNCH_CHECK();
   }
-  wg_transpose_img_kernel<<<dim3(256 / 64, T), 256, 0, s>>>(x2, 256, B, 256, kTN, nullptr, img_x2);
+  wg_transpose_img_kernel<<<dim3(256 / 64, T), 256, 0, s>>>(x2, 256, 0, rows, B, 256, kTN, nullptr, img_x2);
   T2_LAUNCH_CHECK();
-  wg_transpose_img_kernel<<<dim3(512 / 64, T + 1), 256, 0, s>>>(st.ctx, 512, B, 512, kTN, nullptr, img_ctx);
+  wg_transpose_img_kernel<<<dim3(512 / 64, T + 1), 256, 0, s>>>(st.ctx, 512, 0, rows + B, B, 512, kTN, nullptr, img_ctx);
   T2_LAUNCH_CHECK();
-  wg_transpose_img_kernel<<<dim3(1024 / 64, T + 1), 256, 0, s>>>(st.ha, 1024, B, 1024, kTN, nullptr, img_ha);
+  wg_transpose_img_kernel<<<dim3(1024 / 64, T + 1), 256, 0, s>>>(st.ha, 1024, 0, rows + B, B, 1024, kTN, nullptr, img_ha);
   T2_LAUNCH_CHECK();
-  wg_transpose_img_kernel<<<dim3(1024 / 64, T + 1), 256, 0, s>>>(st.hd, 1024, B, 1024, kTN, nullptr, img_hd);
+  wg_transpose_img_kernel<<<dim3(1024 / 64, T + 1), 256, 0, s>>>(st.hd, 1024, 0, rows + B, B, 1024, kTN, nullptr, img_hd);
   T2_LAUNCH_CHECK();
   // job table: LSTM l, feature tile j (of its concatenated input), gate tile i, K split sp
   struct Grp { const uint8_t* img; int ntile; int t0; };   // feature group: image, 256-row tiles per chunk, first chunk
@@ -275,16 +272,7 @@ int wgrad_tc_run(T2Model* m, int B, int T, const float* dga, const float* dgd, c
           }
   }
   if (jobs.size() > 8192) return fail(T2_ERR_UNSUPPORTED, "wgrad: too many jobs (T too long)");
-  T2_CUDA(cudaMemcpyAsync(jobs_d, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s));
-  T2_CUDA(cudaStreamSynchronize(s));            // the host vector must outlive the copy
-  const size_t smem = (size_t)kWgStages * kStageB + 256;
-  static bool attr = false;
-  if (!attr) {
-    T2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  wgrad_tc_kernel<<<(unsigned)jobs.size(), kWgThreads, smem, s>>>(jobs_d);
-  T2_LAUNCH_CHECK();
+  T2_TRY(wg_run_jobs(jobs, jobs_d, s));
   {
     const long n = (long)4096 * 1792;
     wg_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part_l[0], nsplit, 1792, 768, G[W_ARNN_WIH], G[W_ARNN_WHH]);
@@ -295,6 +283,38 @@ int wgrad_tc_run(T2Model* m, int B, int T, const float* dga, const float* dgd, c
     wg_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part_l[1], nsplit, 2560, 1536, G[W_DRNN_WIH], G[W_DRNN_WHH]);
     T2_LAUNCH_CHECK();
   }
+  return T2_OK;
+}
+
+
+// ---- generic entry points (also used by the conv-stack weight gradients in train_layers.cu) ------------------------
+int wg_run_jobs(const std::vector<WgJob>& jobs, WgJob* jobs_dev, cudaStream_t s) {
+  if (jobs.empty()) return T2_OK;
+  T2_CUDA(cudaMemcpyAsync(jobs_dev, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s));
+  T2_CUDA(cudaStreamSynchronize(s));            // the host vector must outlive the copy
+  const size_t smem = (size_t)kWgStages * kStageB + 256;
+  static bool attr = false;
+  if (!attr) {
+    T2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  wgrad_tc_kernel<<<(unsigned)jobs.size(), kWgThreads, smem, s>>>(jobs_dev);
+  T2_LAUNCH_CHECK();
+  return T2_OK;
+}
+size_t wg_colstats_ws_bytes(int C) { return (size_t)kStatSplit * 2 * C * sizeof(float); }
+int wg_colstats(const float* x, long rows, int C, float* stat_ws, float* scale, float* inv_scale, float* colsum, cudaStream_t s) {
+  wg_colstats_kernel<<<dim3((C + 31) / 32, kStatSplit), 256, 0, s>>>(x, rows, C, stat_ws);
+  T2_LAUNCH_CHECK();
+  wg_colstats_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stat_ws, C, scale, inv_scale, colsum);
+  T2_LAUNCH_CHECK();
+  return T2_OK;
+}
+int wg_transpose_images(const float* src, long ld, long row0, long rows_total, int chunk_rows, int nchunks, int C, int TR,
+                        const float* scale, uint8_t* img, cudaStream_t s) {
+  const int ntile = (C + TR - 1) / TR;
+  wg_transpose_img_kernel<<<dim3(ntile * TR / 64, nchunks), 256, 0, s>>>(src, ld, row0, rows_total, chunk_rows, C, TR, scale, img);
+  T2_LAUNCH_CHECK();
   return T2_OK;
 }
 
