@@ -46,7 +46,7 @@ struct ConvParams {
   const float* scale; const float* shift;     // per output channel
   int act, out_mode, cout;
   __half* out_planes; long out_plane_rows;
-  float* out_f32; long ldo;
+  float* out_f32; long ldo; int out_seq_rows;  // out_mode 1: row of (b, t) = b * out_seq_rows + t
   const float* residual; long res_batch_stride; const int32_t* row_len;
   int cluster;
 };
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
             }
           }
         } else if (valid && p.out_mode == 1) {   // fp32 rows (b*T + t, ldo)
-          float* o = p.out_f32 + ((long)b * p.T + pt) * p.ldo + n0 + c0;
+          float* o = p.out_f32 + ((long)b * p.out_seq_rows + pt) * p.ldo + n0 + c0;
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         } else if (valid && p.out_mode == 2) {   // (B, cout, T) + residual (B, T, cout), masked beyond row_len
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_tc_kernel(const ConvParams 
 // and channels >= C are zero; every row of every plane (incl. guards) is written.
 __global__ void rows_to_planes_kernel(const float* __restrict__ x, long batch_stride, int C, int c_pad,
                                       const int32_t* __restrict__ len, int B, int T, __half* __restrict__ planes,
-                                      long plane_rows) {
+                                      long plane_rows, const float* __restrict__ in_scale) {
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;     // plane row (incl. 2 guard rows)
   const int g = blockIdx.y;
   if (row >= plane_rows) return;
@@ -240,10 +240,11 @@ __global__ void rows_to_planes_kernel(const float* __restrict__ x, long batch_st
   int b = -1, t = -1;
   if (prow >= 0) { b = (int)(prow / span); t = (int)(prow - (long)b * span) - 2; }
   const bool valid = b >= 0 && b < B && t >= 0 && t < T && (len == nullptr || t < len[b]);
+  const float mul = in_scale ? *in_scale : 1.f;       // power-of-two pre-scale (gradients do not fit fp16 otherwise)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = g * 8 + i;
-    const float v = (valid && c < C) ? x[(long)b * batch_stride + (long)t * C + c] : 0.f;
+    const float v = (valid && c < C) ? x[(long)b * batch_stride + (long)t * C + c] * mul : 0.f;
     split_fp16(v, hh[i], ll[i]);
   }
   __half* dst = planes + (((long)g * 2) * plane_rows + row) * 8;
@@ -343,13 +344,17 @@ int tc_pack_weights(const float* w, int cout, int cin, int taps, int nt_rows, ui
   return T2_OK;
 }
 
-int tc_rows_to_planes(const float* x, long batch_stride, int C, int c_pad, const int32_t* len, int B, int T,
-                      __half* planes, cudaStream_t s) {
+int tc_rows_to_planes_scaled(const float* x, long batch_stride, int C, int c_pad, const int32_t* len, int B, int T,
+                             __half* planes, const float* in_scale, cudaStream_t s) {
   const long rows = tc_plane_rows(B, T);
   rows_to_planes_kernel<<<dim3((unsigned)((rows + 127) / 128), c_pad / 8), 128, 0, s>>>(x, batch_stride, C, c_pad, len, B, T,
-                                                                                      planes, rows);
+                                                                                      planes, rows, in_scale);
   T2_LAUNCH_CHECK();
   return T2_OK;
+}
+int tc_rows_to_planes(const float* x, long batch_stride, int C, int c_pad, const int32_t* len, int B, int T,
+                      __half* planes, cudaStream_t s) {
+  return tc_rows_to_planes_scaled(x, batch_stride, C, c_pad, len, B, T, planes, nullptr, s);
 }
 
 int tc_embed_to_planes(const int64_t* text, const float* emb, int n_symbols, int B, int T, __half* planes,
@@ -376,7 +381,8 @@ int tc_conv(const TcConvArgs& a, cudaStream_t s) {
   p.n_tiles_m = (int)((p.in_plane_rows - 4) / kTile);
   p.scale = a.scale; p.shift = a.shift; p.act = a.act; p.out_mode = a.out_mode; p.cout = a.cout;
   p.out_planes = a.out_planes; p.out_plane_rows = p.in_plane_rows;
-  p.out_f32 = a.out_f32; p.ldo = a.ldo; p.residual = a.residual; p.row_len = a.row_len;
+  p.out_f32 = a.out_f32; p.ldo = a.ldo; p.out_seq_rows = a.out_seq_rows > 0 ? a.out_seq_rows : a.T;
+  p.residual = a.residual; p.row_len = a.row_len;
   p.res_batch_stride = a.res_batch_stride ? a.res_batch_stride : (long)a.T * a.cout;
   const char* e = getenv("T2_CONV_CLUSTER");
   p.cluster = e ? atoi(e) : 2;

@@ -16,6 +16,7 @@ struct TcConvArgs {
   int out_mode;                           // 0 planes, 1 fp32 rows (B*T, ldo), 2 fp32 (B, cout, T) + residual
   __half* out_planes;
   float* out_f32; long ldo;
+  int out_seq_rows;                       // out_mode 1: output row of (b, t) = b * out_seq_rows + t (0 = T)
   const float* residual; long res_batch_stride; const int32_t* row_len;
 };
 
@@ -24,6 +25,8 @@ size_t tc_planes_bytes(int B, int T, int c_pad);
 int tc_pack_weights(const float* w, int cout, int cin, int taps, int nt_rows, uint8_t** img, cudaStream_t s);
 int tc_rows_to_planes(const float* x, long batch_stride, int C, int c_pad, const int32_t* len, int B, int T,
                       __half* planes, cudaStream_t s);
+int tc_rows_to_planes_scaled(const float* x, long batch_stride, int C, int c_pad, const int32_t* len, int B, int T,
+                             __half* planes, const float* in_scale /* device scalar or null */, cudaStream_t s);
 int tc_embed_to_planes(const int64_t* text, const float* emb, int n_symbols, int B, int T, __half* planes,
                        cudaStream_t s);
 int tc_fold_bn(const float* cbias, const float* g, const float* b, const float* mean, const float* var, float eps,

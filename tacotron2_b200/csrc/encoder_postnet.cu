@@ -341,7 +341,7 @@ int encoder_forward(T2Model* m, const T2EncoderArgs* a, cudaStream_t s) {
   if (a->stash) {
     // autograd path: fp32 conv stack with the activations kept for the backward pass (train_layers.cu)
     const float* xl = nullptr;
-    T2_TRY(encoder_convs_train(m, a, s, &xl, &st_gates, &st_c));
+    T2_TRY(encoder_convs_train(m, a, s, &xl, &st_gates, &st_c, pl0));
     GemmArgs g;
     g.seg[0] = {xl, kEnc, m->enc_lstm_wih, kEnc, kEnc};
     g.M = B * T; g.N = 8 * kEncH; g.C = gin; g.ldc = 8 * kEncH; g.bias = m->enc_lstm_b;

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "conv_tc.h"
 #include "decoder.h"
 #include "gemm_f32.cuh"
 #include "train_layers.h"
@@ -278,7 +279,57 @@ struct ConvLayer {
   const float* wpk;                  // packed fp32 weights (cout, 5, cin)
   int wbase;                         // index of conv.weight in the state_dict table
   uint32_t site; const uint8_t* keep;
+  const uint8_t* wimg_fwd;           // tensor-core weight image of the forward conv (conv_tc.cu), packed by pack_model
+  uint8_t** wimg_dgrad;              // storage of the flipped / transposed image of the input-gradient conv
 };
+// tensor-core conv path of the training forward / input gradient: planes scratch (null = plain cuBLAS GEMMs)
+struct TcTrain { __half* planes; };
+// T2_CONV_TRAIN: which training-mode convolutions run on the tensor-core engine (conv_tc.cu) instead of plain cuBLAS fp32
+// GEMMs.  Default "dgrad": the input gradients only -- the forward through it measured 2e-2 gradient error on one
+// ill-conditioned test shape (near-constant BatchNorm channels amplify its ~1e-5 output error), so the training forward
+// stays fp32 until that is understood; "both" / "fwd" / "cublas" select the other combinations.
+int tc_train_mode() {
+  const char* e = getenv("T2_CONV_TRAIN");
+  if (!e) return 2;
+  if (e[0] == 'b') return 3;
+  if (e[0] == 'c') return 0;
+  if (e[0] == 'f') return 1;
+  if (e[0] == 'd') return 2;
+  return 3;
+}
+bool use_tc_train() { return tc_train_mode() != 0; }
+// Wd[ci][co][k'] = W[co][ci][4 - k']: the input gradient of a k=5 'same' conv is a conv of G_z with this kernel
+__global__ void flip_conv_w_kernel(const float* __restrict__ w, float* __restrict__ wd, int cout, int cin) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)cout * cin * kConvK) return;
+  const int k = (int)(i % kConvK); const long r = i / kConvK; const int ci = (int)(r % cin); const int co = (int)(r / cin);
+  wd[((long)ci * cout + co) * kConvK + (kConvK - 1 - k)] = w[i];
+}
+// s_g = the smallest per-channel power-of-two scale (= the scale of the largest channel); out_vec[0..512) = 1 / s_g
+__global__ void global_scale_kernel(const float* __restrict__ scale, int C, float* __restrict__ s_g, float* __restrict__ out_vec) {
+  __shared__ float sm;
+  if (threadIdx.x == 0) {
+    float m = scale[0];
+    for (int i = 1; i < C; ++i) m = fminf(m, scale[i]);
+    sm = m; *s_g = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) out_vec[i] = 1.f / sm;
+}
+int tc_train_conv(T2Model* m, const float* xp, int cin, const uint8_t* wimg, int cout, int B, int T, float* outp, __half* planes,
+                  const float* in_scale, const float* out_scale, cudaStream_t s) {
+  // outp[padded rows][cout] = conv_k5(xp[padded rows][cin]) (no bias), split-fp16 tensor-core engine; the input may be
+  // pre-scaled by the device scalar *in_scale (a power of two) with out_scale[c] = 1 / *in_scale undoing it
+  const int c_pad = cin < 128 ? 128 : cin;
+  T2_TRY(tc_rows_to_planes_scaled(xp + (long)kPadRows * cin, (long)(T + 2 * kPadRows) * cin, cin, c_pad, nullptr, B, T, planes,
+                                  in_scale, s));
+  TcConvArgs c;
+  memset(&c, 0, sizeof(c));
+  c.in = planes; c.cin_pad = c_pad; c.wimg = wimg; c.taps = kConvK; c.B = B; c.T = T; c.cout = cout; c.nt_rows = cout >= 128 ? 128 : 80;
+  c.scale = out_scale ? out_scale : m->ones; c.shift = m->zeros; c.act = 0; c.out_mode = 1;
+  c.out_f32 = outp + (long)kPadRows * cout; c.ldo = cout; c.out_seq_rows = T + 2 * kPadRows;
+  return tc_conv(c, s);
+}
 
 // ---- conv weight gradient on the tcgen05 engine (wgrad_tc.cu) ---------------------------------------------------------
 // dW_k[co][ci] = sum_r G_z[r][co] X[r + k - 2][ci]: K = padded rows in chunks of 64, A = G_z^T images (per-channel power-of-two
@@ -350,12 +401,16 @@ int conv_wgrad_tc(const ConvLayer& L, int B, int T, const float* gz_p, const flo
 }
 
 int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* xp, float* zp,
-             float* stats, float* yp, float* y_plain, bool update_running, float* partial, cudaStream_t s) {
+             float* stats, float* yp, float* y_plain, bool update_running, float* partial, const TcTrain* tc, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
-  for (int k = 0; k < kConvK; ++k)
-    T2_TRY(gemm_rm(bl, false, true, Me, L.cout, L.cin, xp + (long)k * L.cin, L.cin, L.wpk + (long)k * L.cin, (long)kConvK * L.cin,
-                   zp + (long)kPadRows * L.cout, L.cout, k ? 1.f : 0.f));
+  if (tc && (tc_train_mode() & 1)) {
+    T2_TRY(tc_train_conv(m, xp, L.cin, L.wimg_fwd, L.cout, B, T, zp, tc->planes, nullptr, nullptr, s));
+  } else {
+    for (int k = 0; k < kConvK; ++k)
+      T2_TRY(gemm_rm(bl, false, true, Me, L.cout, L.cin, xp + (long)k * L.cin, L.cin, L.wpk + (long)k * L.cin, (long)kConvK * L.cin,
+                     zp + (long)kPadRows * L.cout, L.cout, k ? 1.f : 0.f));
+  }
   {
     float* rm = const_cast<float*>(m->w[L.wbase + 4]); float* rv = const_cast<float*>(m->w[L.wbase + 5]);
     const long M = (long)B * T;
@@ -383,7 +438,7 @@ int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
 // non-null, and the gradients of conv.weight / conv.bias / bn.weight / bn.bias.
 int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* g, int g_padded,
              const float* xp, const float* zp, const float* stats, const float* yp, float* gz_p, float* gx_p, float* sums, float* dwpk,
-             const float* ones, float* const* G, const WgConvWs* wg, cudaStream_t s) {
+             const float* ones, float* const* G, const WgConvWs* wg, const TcTrain* tc, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
   float* partial = sums + 2 * L.cout;      // (kRedSplit, 2, cout) scratch behind the two result rows
@@ -412,7 +467,17 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
       T2_LAUNCH_CHECK();
     }
   }
-  if (gx_p) {
+  if (gx_p && tc && wg && (tc_train_mode() & 2)) {   // input gradient = conv of G_z with the flipped / transposed kernel on the tensor-core engine
+    // G_z is pre-scaled by a power of two (from the per-channel statistics of the weight-gradient pass): fp16 range
+    global_scale_kernel<<<1, 256, 0, s>>>(wg->scale, L.cout, wg->colsum, wg->stat);      // colsum[0] = s_g, stat[0..512) = 1 / s_g
+    T2_LAUNCH_CHECK();
+    if (!m->dgrad_tmp) T2_CUDA(cudaMalloc((void**)&m->dgrad_tmp, (size_t)kPost * kPost * kConvK * 4));
+    const long nw = (long)L.cout * L.cin * kConvK;
+    flip_conv_w_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(m->w[L.wbase], m->dgrad_tmp, L.cout, L.cin);
+    T2_LAUNCH_CHECK();
+    T2_TRY(tc_pack_weights(m->dgrad_tmp, L.cin, L.cout, kConvK, L.cin >= 128 ? 128 : 80, L.wimg_dgrad, s));
+    T2_TRY(tc_train_conv(m, gz_p, L.cout, *L.wimg_dgrad, L.cin, B, T, gx_p, tc->planes, wg->colsum, wg->stat, s));
+  } else if (gx_p) {
     for (int k = 0; k < kConvK; ++k)
       T2_TRY(gemm_rm(bl, false, false, Me, L.cin, L.cout, gz_p + (long)(2 * kPadRows - k) * L.cout, L.cout, L.wpk + (long)k * L.cin,
                      (long)kConvK * L.cin, gx_p + (long)kPadRows * L.cin, L.cin, k ? 1.f : 0.f));
@@ -562,6 +627,7 @@ static void post_layers(T2Model* m, int training, const uint8_t* keep, int B, in
     L[i].cin = kPostCh[i]; L[i].cout = kPostCh[i + 1]; L[i].act = i == 4 ? ACT_NONE : ACT_TANH; L[i].dropout = training;
     L[i].wpk = m->post_conv_w[i]; L[i].wbase = W_POST_CONV0 + 7 * i; L[i].site = 2000 + i;
     L[i].keep = (training && keep) ? keep + (size_t)i * B * kPost * T : nullptr;     // [(B,512,T)] x 4 + (B,80,T)
+    L[i].wimg_fwd = m->tc_post_conv[i]; L[i].wimg_dgrad = &m->tc_dgrad_post[i];
   }
 }
 
@@ -580,9 +646,14 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
   T2_LAUNCH_CHECK();
   ConvLayer L[5];
   post_layers(m, a->training, a->keep, B, T, L);
+  TcTrain tcw; const TcTrain* tc = nullptr;
+  if (use_tc_train()) {   // a->ws is at least postnet_ws_bytes(): room for the input planes of one layer
+    if (a->ws_bytes < tc_planes_bytes(B, T, kPost) + 512) return fail(T2_ERR_WORKSPACE, "postnet workspace too small");
+    tcw.planes = (__half*)a256((size_t)a->ws); tc = &tcw;
+  }
   for (int i = 0; i < 5; ++i)
     T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.x[i], st.z[i], st.stats[i], st.x[i + 1], nullptr, a->training != 0,
-                    st.stats[i] + 2 * L[i].cout, s));
+                    st.stats[i] + 2 * L[i].cout, tc, s));
   rows_to_bct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.x[5], a->add_residual ? st.x[0] : nullptr, a->mel_post, B, T, kMel);
   T2_LAUNCH_CHECK();
   return T2_OK;
@@ -591,7 +662,7 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
 size_t postnet_backward_ws_bytes(int B, int T) {
   const size_t Mp = (size_t)B * (T + 2 * kPadRows);
   return 3 * a256(Mp * kPost * 4) + a256((size_t)B * T * kMel * 4) + a256(Mp * 4) + a256((size_t)kPost * kPost * kConvK * 4) +
-         a256((size_t)(2 + 2 * kRedSplit) * kPost * 4) + wgconv_bytes(B, T, nullptr, nullptr) + 4096;
+         a256((size_t)(2 + 2 * kRedSplit) * kPost * 4) + wgconv_bytes(B, T, nullptr, nullptr) + a256(tc_planes_bytes(B, T, kPost)) + 8192;
 }
 
 int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
@@ -615,6 +686,9 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
     const char* e = getenv("T2_WGRAD");
     if (!(e && e[0] == 'c')) { wgconv_bytes(B, T, &wgws, (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023)); wg = &wgws; }
   }
+  p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023) + wgconv_bytes(B, T, nullptr, nullptr);
+  TcTrain tcw; const TcTrain* tc = nullptr;
+  if (use_tc_train()) { tcw.planes = (__half*)a256((size_t)p); tc = &tcw; }
   cublasHandle_t bl;
   T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)Mp);
@@ -632,7 +706,7 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
       T2_LAUNCH_CHECK();
     }
     T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.x[i], st.z[i], st.stats[i], st.x[i + 1], gz, gx, sums, dwpk,
-                    ones, a->grads, wg, s));
+                    ones, a->grads, wg, tc, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;
   }
@@ -653,11 +727,12 @@ static void enc_layers(T2Model* m, int training, const uint8_t* keep, int B, int
     L[i].cin = kEnc; L[i].cout = kEnc; L[i].act = ACT_RELU; L[i].dropout = training;
     L[i].wpk = m->enc_conv_w[i]; L[i].wbase = W_ENC_CONV0 + 7 * i; L[i].site = 1000 + i;
     L[i].keep = (training && keep) ? keep + (size_t)i * B * kEnc * T : nullptr;
+    L[i].wimg_fwd = m->tc_enc_conv[i]; L[i].wimg_dgrad = &m->tc_dgrad_enc[i];
   }
 }
 
 // conv stack of the training forward: fills the stash and returns the LSTM input rows (B*T, 512)
-int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, const float** xl, float** gates, float** cst) {
+int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, const float** xl, float** gates, float** cst, void* planes) {
   const int B = a->B, T = a->T;
   if (a->stash_bytes < encoder_stash_bytes(B, T)) return fail(T2_ERR_WORKSPACE, "encoder stash too small");
   EncStash st;
@@ -672,9 +747,11 @@ int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, cons
   T2_LAUNCH_CHECK();
   ConvLayer L[3];
   enc_layers(m, a->training, a->keep, B, T, L);
+  TcTrain tcw; const TcTrain* tc = nullptr;
+  if (use_tc_train() && planes) { tcw.planes = (__half*)planes; tc = &tcw; }
   for (int i = 0; i < 3; ++i)
     T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], i == 2 ? st.xl : nullptr,
-                    a->training != 0, st.cs.stats[i] + 2 * L[i].cout, s));
+                    a->training != 0, st.cs.stats[i] + 2 * L[i].cout, tc, s));
   *xl = st.xl; *gates = st.gates; *cst = st.cst;
   return T2_OK;
 }
@@ -692,7 +769,7 @@ size_t encoder_backward_ws_bytes(int B, int T) {
   return a256((size_t)B * T * 8 * kEncH * 4) + a256((size_t)B * T * kEnc * 4) * 2 + a256((size_t)2 * nsplit * 64 * kEncH * 4) +
          a256((size_t)2 * 64 * kEncH * 4) + 3 * a256(Mp * kEnc * 4) + a256((Mp > (size_t)B * T ? Mp : (size_t)B * T) * 4) +
          a256((size_t)kEnc * kEnc * kConvK * 4) + a256((size_t)(2 + 2 * kRedSplit) * kEnc * 4) + a256(8 * kEncH * 4) +
-         wgconv_bytes(B, T, nullptr, nullptr) + 4096;
+         wgconv_bytes(B, T, nullptr, nullptr) + a256(tc_planes_bytes(B, T, kEnc)) + 8192;
 }
 
 int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
@@ -724,6 +801,9 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
     const char* e = getenv("T2_WGRAD");
     if (!(e && e[0] == 'c')) { wgconv_bytes(B, T, &wgws, (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023)); wg = &wgws; }
   }
+  p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023) + wgconv_bytes(B, T, nullptr, nullptr);
+  TcTrain tcw; const TcTrain* tc = nullptr;
+  if (use_tc_train()) { tcw.planes = (__half*)a256((size_t)p); tc = &tcw; }
   cublasHandle_t bl;
   T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((n_ones + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)n_ones);
@@ -764,7 +844,7 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   for (int i = 2; i >= 0; --i) {
     const bool need_gx = i > 0 || a->d_embedded || (a->text && G[W_EMB]);
     T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], gz,
-                    need_gx ? gx : nullptr, sums, dwpk, ones, G, wg, s));
+                    need_gx ? gx : nullptr, sums, dwpk, ones, G, wg, tc, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;
   }
