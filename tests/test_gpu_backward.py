@@ -235,3 +235,49 @@ def test_fused_clip_adam_matches_torch():
     with torch.no_grad():
         after = model.inference(text)[0]
     assert not torch.equal(before, after)
+
+
+def test_checkpoint_round_trip_like_train_py(tmp_path):
+    """train.py:99-113: save {'state_dict', 'optimizer'} after a few steps, load into fresh objects, and the next step is
+    bit-identical (fused optimizer state included)."""
+    import tacotron2_b200._engine as E
+    hp = t2.create_hparams()
+    g = torch.Generator().manual_seed(1)
+    text = torch.randint(0, 148, (4, 12), generator=g).cuda()
+    tl = torch.tensor([12, 11, 9, 7]).cuda()
+    ol = torch.tensor([10, 14, 8, 14]).cuda()
+    mels = torch.randn(4, 80, 14, generator=g).cuda()
+    gt = torch.zeros(4, 14).cuda()
+    for i, n in enumerate(ol.tolist()):
+        mels[i, :, n:] = 0
+        gt[i, n - 1:] = 1
+    x, y = (text, tl, mels, 12, ol), (mels, gt)
+    crit = t2.Tacotron2Loss()
+
+    def step(model, opt):
+        model.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step(max_norm=hp.grad_clip_thresh)
+        return loss.item()
+
+    torch.manual_seed(3)
+    model = t2.Tacotron2(hp).cuda().train()
+    opt = t2.FusedClipAdam(model.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+    E._seed_counter[0] = 0
+    losses = [step(model, opt) for _ in range(3)]
+    assert losses[2] < losses[0]
+    path = str(tmp_path / "ckpt")
+    torch.save({"iteration": 3, "state_dict": model.state_dict(), "optimizer": opt.state_dict(), "learning_rate": hp.learning_rate}, path)
+    counter = E._seed_counter[0]
+    a = step(model, opt)
+    ck = torch.load(path, map_location="cpu")
+    model2 = t2.Tacotron2(hp).cuda().train()
+    model2.load_state_dict(ck["state_dict"])
+    opt2 = t2.FusedClipAdam(model2.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+    opt2.load_state_dict(ck["optimizer"])
+    E._seed_counter[0] = counter                      # same Philox dropout streams as the original's 4th step
+    b = step(model2, opt2)
+    assert a == b
+    for p1, p2 in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(p1, p2)

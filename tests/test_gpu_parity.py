@@ -192,3 +192,24 @@ def test_persistent_decoder_is_bit_reproducible():
             outs.append([x.clone() for x in model.decoder.inference(memory)])
     for o in outs[1:]:
         assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+
+
+def test_half_model_inference_like_the_notebook():
+    """inference.ipynb:89-90 does model.cuda().eval().half(): tensors crossing the nn.Module boundaries (embedding, encoder
+    output, mel) are half like in the reference, the kernels compute in their fp32-grade mode from the half-rounded weights.
+    Outputs are half tensors within half-precision distance of the float model holding the same rounded weights."""
+    sd = synth_state_dict(9, gate_bias=-10.0, scale=2.0)
+    sd_r = {k: (v.half().float() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    text = rand_text(2, 17, 4).cuda()
+    keep = keep_mask((8, 2, 2, 256), 0.5, 6)
+    outs = []
+    for half in (False, True):
+        model = make_model(sd_r if not half else sd, 8)
+        if half:
+            model = model.half()
+        with torch.no_grad(), t2.dropout_masks(prenet=keep):
+            o = model.inference(text)
+        outs.append(o)
+        assert all(x.dtype == (torch.float16 if half else torch.float32) for x in o)
+    for a, b in zip(outs[0], outs[1]):
+        assert a.shape == b.shape and rel_err(b.float(), a) < 2e-2
