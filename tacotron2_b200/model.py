@@ -459,6 +459,7 @@ class Tacotron2(nn.Module, _EngineOwner):
                                       *[p_ for _, p_ in named])
         else:
             memory = eng.encoder(text=text_inputs, lengths=text_lengths, training=self.training, keep=masks["enc"])
+        memory = memory.to(self._t2_out_dtype())
         mel_outputs, gate_outputs, alignments = self.decoder(memory, mels, memory_lengths=text_lengths)
         mel_btc = mel_outputs.transpose(1, 2)
         if grad:
@@ -484,6 +485,7 @@ class Tacotron2(nn.Module, _EngineOwner):
         the per-row lengths.  B == 1 is exactly the reference."""
         eng = self._t2_engine()
         memory = eng.encoder(text=inputs, lengths=None, training=self.training, keep=current_masks()["enc"])
+        memory = memory.to(self._t2_out_dtype())     # a .half() model hands half tensors between its modules (ipynb:89-90)
         mel_outputs, gate_outputs, alignments = self.decoder.inference(memory)
         lengths = self.decoder.mel_lengths
         self.mel_lengths = lengths
