@@ -281,3 +281,44 @@ def test_checkpoint_round_trip_like_train_py(tmp_path):
     assert a == b
     for p1, p2 in zip(model.parameters(), model2.parameters()):
         assert torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("B,Tt,Tm", [(1, 1, 1), (1, 3, 2), (2, 5, 1), (3, 2, 6)])
+def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
+    """Degenerate sizes: one utterance, one symbol, one frame -- full training step vs the oracle's autograd."""
+    from tests.common import rand_text
+    sd = synth_state_dict(seed=41, scale=2.0)
+    g = torch.Generator().manual_seed(B * 100 + Tt * 10 + Tm)
+    text = rand_text(B, Tt, 3)
+    tl = torch.sort(torch.randint(1, Tt + 1, (B,), generator=g), descending=True)[0]
+    tl[0] = Tt
+    ol = torch.randint(1, Tm + 1, (B,), generator=g)
+    ol[0] = Tm
+    mels = torch.randn(B, 80, Tm, generator=g)
+    gt = torch.zeros(B, Tm)
+    for i, n in enumerate(ol.tolist()):
+        mels[i, :, n:] = 0
+        gt[i, n - 1:] = 1
+    m = dict(pk=keep_mask((Tm + 1, 2, B, 256), 0.5, 1), ak=keep_mask((Tm, B, 1024), 0.1, 2), dk=keep_mask((Tm, B, 1024), 0.1, 3),
+             ek=keep_mask((3, B, 512, Tt), 0.5, 4), qk4=keep_mask((4, B, 512, Tm), 0.5, 5), qk1=keep_mask((B, 80, Tm), 0.5, 6))
+    ref_loss, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    post_keep = [m["qk4"][i] for i in range(4)] + [m["qk1"]]
+    with t2.dropout_masks(prenet=m["pk"], att=m["ak"], dec=m["dk"], enc=m["ek"], post=post_keep):
+        out = model((text.cuda(), tl.cuda(), mels.cuda(), int(tl.max()), ol.cuda()))
+        loss = t2.Tacotron2Loss()(out, (mels.cuda(), gt.cuda()))
+        loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    gmax = max(float(v.abs().max()) for v in ref_g.values())
+    errs = {}
+    for k, p in model.named_parameters():
+        # tiny batches make BatchNorm statistics (1-6 samples per channel) badly conditioned: compare against the largest
+        # gradient of the model rather than each tensor's own maximum
+        errs[k] = float((p.grad.detach().cpu().double() - ref_g[k].double()).abs().max()) / gmax
+    print("minimal train step B=%d T_text=%d T_mel=%d: loss %.5f, worst gradient error / max gradient %.2e" % (B, Tt, Tm, loss.item(), max(errs.values())))
+    # BatchNorm over 1-6 samples per channel: rstd up to 1/sqrt(eps) = 316 amplifies the 1e-5 kernel-level differences
+    bad = {k: v for k, v in errs.items() if not v < 1e-2}
+    assert not bad, bad
