@@ -128,3 +128,43 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         assert int(out[s]) == ctypes.sizeof(cls), s
         for f in fs:
             assert int(out["%s.%s" % (s, f)]) == getattr(cls, f).offset, (s, f)
+
+
+def test_text_mel_collate_matches_reference_semantics():
+    """tacotron2_b200.data_utils.TextMelCollate vs the reference's collate function (data_utils.py:67-111): executed live
+    when /root/reference is present, otherwise checked against its documented properties."""
+    import importlib.util
+    import types
+    from tacotron2_b200.data_utils import TextMelCollate
+    g = torch.Generator().manual_seed(0)
+    batch = []
+    for n_text, n_mel in [(7, 13), (12, 5), (3, 21), (12, 9), (1, 1)]:
+        batch.append((torch.randint(1, 148, (n_text,), generator=g), torch.randn(80, n_mel, generator=g)))
+    for nfs in (1, 2):
+        out = TextMelCollate(nfs)(batch)
+        text, tl, mel, gate, ol = out
+        assert tl.tolist() == sorted(tl.tolist(), reverse=True) and mel.shape[2] % nfs == 0 and mel.shape[2] >= int(ol.max())
+        for i in range(len(batch)):
+            assert int((text[i] != 0).sum()) == int(tl[i]) and bool((mel[i, :, int(ol[i]):] == 0).all())
+            assert gate[i].tolist() == [0.0] * (int(ol[i]) - 1) + [1.0] * (mel.shape[2] - int(ol[i]) + 1)
+        ref_path = "/root/reference/data_utils.py"
+        if not os.path.isfile(ref_path):
+            continue
+        saved = {k: sys.modules.get(k) for k in ("layers", "utils", "text", "librosa", "librosa.filters", "librosa.util",
+                                                 "stft", "audio_processing")}
+        try:
+            for k in ("layers", "utils", "text"):
+                sys.modules[k] = types.ModuleType(k)
+            sys.modules["utils"].load_wav_to_torch = sys.modules["utils"].load_filepaths_and_text = None
+            sys.modules["text"].text_to_sequence = None
+            spec = importlib.util.spec_from_file_location("t2_reference_data_utils", ref_path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        finally:
+            for k, v in saved.items():
+                sys.modules.pop(k, None)
+                if v is not None:
+                    sys.modules[k] = v
+        ref = mod.TextMelCollate(nfs)(batch)
+        for a, b in zip(out, ref):
+            assert a.dtype == b.dtype and torch.equal(a, b)
