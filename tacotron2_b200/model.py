@@ -427,9 +427,11 @@ class Tacotron2(nn.Module, _EngineOwner):
     def parse_batch(self, batch):
         """model.py:473-485."""
         text_padded, input_lengths, mel_padded, gate_padded, output_lengths = batch
+        # the reference reads max_len back from the GPU copy (a device sync, model.py:478); the collate function hands over
+        # host tensors, so take it there and let the (pinned, non_blocking) copies overlap
+        max_len = torch.max(input_lengths.data).item()
         text_padded = to_gpu(text_padded).long()
         input_lengths = to_gpu(input_lengths).long()
-        max_len = torch.max(input_lengths.data).item()
         mel_padded = to_gpu(mel_padded).float()
         gate_padded = to_gpu(gate_padded).float()
         output_lengths = to_gpu(output_lengths).long()

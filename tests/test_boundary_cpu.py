@@ -168,3 +168,15 @@ def test_text_mel_collate_matches_reference_semantics():
         ref = mod.TextMelCollate(nfs)(batch)
         for a, b in zip(out, ref):
             assert a.dtype == b.dtype and torch.equal(a, b)
+
+
+def test_parse_batch_returns_the_reference_structure():
+    """Tacotron2.parse_batch (model.py:473-485) on a collated batch: ((text, input_lengths, mel, max_len, output_lengths),
+    (mel, gate)); on a CPU-only host to_gpu() leaves the tensors where they are."""
+    from tacotron2_b200.data_utils import TextMelCollate
+    g = torch.Generator().manual_seed(1)
+    batch = [(torch.randint(1, 148, (n,), generator=g), torch.randn(80, m, generator=g)) for n, m in [(4, 6), (9, 3), (2, 8)]]
+    model = t2.Tacotron2(t2.create_hparams())
+    x, y = model.parse_batch(TextMelCollate(1)(batch))
+    assert len(x) == 5 and len(y) == 2 and x[3] == 9 and x[0].dtype == torch.int64 and x[2].dtype == torch.float32
+    assert x[1].tolist() == [9, 4, 2] and x[4].tolist() == [3, 6, 8] and torch.equal(x[2], y[0]) and y[1].shape == (3, 8)
