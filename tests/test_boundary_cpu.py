@@ -168,6 +168,12 @@ def test_text_mel_collate_matches_reference_semantics():
         ref = mod.TextMelCollate(nfs)(batch)
         for a, b in zip(out, ref):
             assert a.dtype == b.dtype and torch.equal(a, b)
+        for trial in range(20):                      # random ragged batches (ties in the text lengths included)
+            n = int(torch.randint(1, 9, (1,), generator=g))
+            rb = [(torch.randint(1, 148, (int(torch.randint(1, 12, (1,), generator=g)),), generator=g),
+                   torch.randn(80, int(torch.randint(1, 30, (1,), generator=g)), generator=g)) for _ in range(n)]
+            for a, b in zip(TextMelCollate(nfs)(rb), mod.TextMelCollate(nfs)(rb)):
+                assert a.dtype == b.dtype and torch.equal(a, b)
 
 
 def test_parse_batch_returns_the_reference_structure():
