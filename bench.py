@@ -135,7 +135,8 @@ def cpu_port_sample(threads, dec_steps=60):
         O.postnet(sd, mel)
         t_post = time.perf_counter() - t0
     total = t_enc + T_MEL * step + t_post
-    return {"value": B_PER_GPU * T_MEL / total, "unit": "mel frames/s", "cores": threads, "kind": "port",
+    # cores = the threads actually used (the largest per-component choice; more threads made every component slower)
+    return {"value": B_PER_GPU * T_MEL / total, "unit": "mel frames/s", "cores": max(th_enc, th_dec, th_post), "kind": "port",
             "sample": "oracle port, B=64 T_text=150, fp32, %d host threads available: encoder %.3f s (%d thr) + median of "
                       "%d decoder steps %.1f us/step x800 (%d thr) + postnet T_mel=800 %.3f s (%d thr)"
                       % (threads, t_enc, th_enc, dec_steps, step * 1e6, th_dec, t_post, th_post),
