@@ -5,7 +5,6 @@ Tolerance (north_star): mel frames within 1e-3 relative fp32 -- measured as max|
 and stop decisions (mel_lengths) bit-exact.  The engine is expected to land ~1e-5."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

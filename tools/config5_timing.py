@@ -1,7 +1,7 @@
 """BASELINE.json configs[4] (long-sequence inference B=256, T_text=300, max_decoder_steps=2000, batch-sharded over 8 GPUs):
 times the per-GPU share (B=32) and the whole batch on ONE GPU (4 consecutive 64-row launches), checks the outputs are finite
 and that B=32 rows equal the first 32 rows of... (rows are independent) a B=64 run with the same masks."""
-import os, sys, time
+import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tacotron2_b200 as t2

@@ -2,7 +2,6 @@
     python tools/decoder_train_timing.py [B] [T_enc] [T_mel]"""
 import os
 import sys
-import time
 
 import torch
 
