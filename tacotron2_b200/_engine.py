@@ -80,6 +80,12 @@ def bump_weights_generation():
     _weights_generation[0] += 1
 
 
+def invalidate_weights():
+    """Public: every engine re-packs its device-side weight copies on its next call (use after in-place parameter writes
+    that bypass torch's version counter, e.g. ``p.data.copy_()`` for EMA / SWA / weight surgery)."""
+    bump_weights_generation()
+
+
 _seed_counter = [0]
 
 
@@ -113,8 +119,15 @@ class Engine:
         self.impl = _capi.IMPL_AUTO
 
     # -- weights ---------------------------------------------------------------------------------
-    def ensure(self, named):
-        """named: dict full-name -> tensor (missing entries are replaced by zeros)."""
+    def invalidate(self):
+        """Forget the cache key: the next call re-packs every device-side copy from the live parameters."""
+        self.key = None
+
+    def ensure(self, named, force=False):
+        """named: dict full-name -> tensor (missing entries are replaced by zeros).  The packed copies are rebuilt when the
+        key (global generation, per-tensor pointer / torch version counter / dtype) changed or when `force` is set.
+        Writes through ``.data`` do not move torch's version counter: callers doing that use
+        ``model.invalidate_weights()`` / ``tacotron2_b200.invalidate_weights()``."""
         dev = None
         for t in named.values():
             if t.is_cuda:
@@ -125,7 +138,7 @@ class Engine:
                                "CPU path -- call .cuda() first")
         key = (_weights_generation[0],) + tuple(
             (named[n].data_ptr(), named[n]._version, named[n].dtype) if n in named else None for n, _ in self.spec)
-        if self.handle is not None and key == self.key and dev == self.device:
+        if self.handle is not None and key == self.key and dev == self.device and not force:
             return
         L = _capi.lib()
         held, ptrs = [], (C.c_void_p * _capi.T2_NUM_WEIGHTS)()

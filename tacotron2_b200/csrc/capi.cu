@@ -273,6 +273,12 @@ int t2_decoder_run(T2Model* m, const T2DecoderArgs* a, void* stream) {
     if (!persistent_supported(m, a)) return fail(T2_ERR_UNSUPPORTED, "persistent decoder does not support this shape/mode");
     return decoder_run_persistent(m, a, (cudaStream_t)stream);
   }
+  // only the persistent kernel writes the training stash: a backward pass over a stash the stepwise path left
+  // untouched would silently produce garbage gradients
+  if (a->stash)
+    return fail(T2_ERR_UNSUPPORTED, "decoder: the training stash needs the persistent implementation (%s)",
+                a->impl == T2_IMPL_STEPWISE ? "impl = STEPWISE was requested"
+                                            : "this shape / device does not fit it: T_enc too large for shared memory or < 128 SMs");
   return decoder_run_stepwise(m, a, (cudaStream_t)stream);
 }
 

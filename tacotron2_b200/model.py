@@ -62,8 +62,39 @@ class _EngineOwner(object):
         root = ref() if ref is not None else None
         return root if root is not None else self
 
+    def _t2_link(self):
+        """(Re-)point the children at this module as their engine owner.  The links are weak references kept out of
+        copies / pickles (__getstate__ below), so they are rebuilt lazily: a deepcopy of a Tacotron2 must resolve ITS OWN
+        parameters, not the original's."""
+        ref = None
+        for child in self._t2_children():
+            cur = child.__dict__.get("_t2_root_ref")
+            if cur is None or cur() is not self:
+                if ref is None:
+                    ref = weakref.ref(self)
+                child.__dict__["_t2_root_ref"] = ref
+
+    def _t2_children(self):
+        return ()
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model): the engine (a ctypes handle + device workspaces) and the weak
+        # back-references are per-instance runtime state; the copy builds its own on first use
+        state = dict(super().__getstate__())       # nn.Module.__getstate__ (the mixin precedes nn.Module in the MRO)
+        state.pop("_t2_root_ref", None)
+        state.pop("_t2_engine_obj", None)
+        return state
+
+    def invalidate_weights(self):
+        """Call after writing parameters / buffers in a way torch's version counter does not see (``p.data.copy_()``,
+        ``p.data.mul_()``, raw pointer writes): the packed device-side operand images are rebuilt on the next call."""
+        eng = self._t2_root().__dict__.get("_t2_engine_obj")
+        if eng is not None:
+            eng.invalidate()
+
     def _t2_engine(self):
         root = self._t2_root()
+        root._t2_link()
         eng = root.__dict__.get("_t2_engine_obj")
         if eng is None:
             eng = Engine(root._t2_hparams)
@@ -76,7 +107,10 @@ class _EngineOwner(object):
             named[prefix + k] = v
         for k, v in root.named_buffers():
             named[prefix + k] = v
-        eng.ensure(named)
+        # under autograd in training mode the parameters change every step (possibly through .data, which the version
+        # counter does not see): always re-pack there; otherwise the (pointer, version, dtype) key decides
+        eng.ensure(named, force=root.training and torch.is_grad_enabled() and
+                   any(p_.requires_grad for p_ in root.parameters()))
         return eng
 
     def _t2_out_dtype(self):
@@ -85,11 +119,16 @@ class _EngineOwner(object):
         return torch.float32
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    """load_state_dict copies into the parameters through .data-like paths: re-pack on the next call."""
+    module.invalidate_weights()
+
+
 def _require_no_grad(module, what):
     if torch.is_grad_enabled() and any(p_.requires_grad for p_ in module.parameters()):
         raise NotImplementedError(
-            "tacotron2_b200: %s under autograd is not implemented in this round (forward-only "
-            "engine); wrap the call in torch.no_grad()" % what)
+            "tacotron2_b200: %s on its own has no autograd node (the prenet's backward is part of Decoder.forward's, "
+            "model.py:396-399); call it through Decoder.forward / Tacotron2.forward or under torch.no_grad()" % what)
 
 
 def _wants_grad(module, *tensors):
@@ -163,7 +202,7 @@ class _PostnetFn(torch.autograd.Function):
                                                                           zip(sv["names"], sv["params"]))
 
 
-class Prenet(nn.Module, _EngineOwner):
+class Prenet(_EngineOwner, nn.Module):
     """model.py:89-100.  Dropout(0.5) is always on, as in the reference (model.py:99)."""
     _t2_prefix = "decoder.prenet."
 
@@ -184,7 +223,7 @@ class Prenet(nn.Module, _EngineOwner):
         return out.reshape(*shp[:-1], out.shape[-1]).to(x.dtype)
 
 
-class Postnet(nn.Module, _EngineOwner):
+class Postnet(_EngineOwner, nn.Module):
     """model.py:103-146: five conv1d(k=5) + BatchNorm1d, tanh on the first four."""
     _t2_prefix = "postnet."
 
@@ -228,7 +267,7 @@ class Postnet(nn.Module, _EngineOwner):
         return self._run(x, None, False)
 
 
-class Encoder(nn.Module, _EngineOwner):
+class Encoder(_EngineOwner, nn.Module):
     """model.py:149-201: 3 x (conv1d k5 + BatchNorm1d + ReLU [+dropout]) then a BiLSTM."""
     _t2_prefix = "encoder."
 
@@ -266,7 +305,7 @@ class Encoder(nn.Module, _EngineOwner):
         return self._run(x, None)
 
 
-class Decoder(nn.Module, _EngineOwner):
+class Decoder(_EngineOwner, nn.Module):
     """model.py:204-454."""
     _t2_prefix = "decoder."
 
@@ -298,7 +337,10 @@ class Decoder(nn.Module, _EngineOwner):
         self.gate_layer = LinearNorm(hparams.decoder_rnn_dim + hparams.encoder_embedding_dim, 1,
                                      bias=True, w_init_gain='sigmoid')
         self.mel_lengths = None        # (B,) int32 after inference(): frames per row (stop latch)
-        self.prenet.__dict__["_t2_root_ref"] = weakref.ref(self)
+        self._t2_link()
+
+    def _t2_children(self):
+        return (self.prenet,)
 
     def get_go_frame(self, memory):
         """model.py:243-256."""
@@ -402,7 +444,7 @@ class _DecoderFn(torch.autograd.Function):
         return (None, d_memory.to(ctx.mem_dtype), None, None) + tuple(grads[n].to(p_.dtype) for n, p_ in named)
 
 
-class Tacotron2(nn.Module, _EngineOwner):
+class Tacotron2(_EngineOwner, nn.Module):
     """model.py:457-529."""
 
     def __init__(self, hparams):
@@ -419,10 +461,12 @@ class Tacotron2(nn.Module, _EngineOwner):
         self.encoder = Encoder(hparams)
         self.decoder = Decoder(hparams)
         self.postnet = Postnet(hparams)
-        ref = weakref.ref(self)
-        for child in (self.encoder, self.decoder, self.postnet, self.decoder.prenet):
-            child.__dict__["_t2_root_ref"] = ref
         self.mel_lengths = None
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
+        self._t2_link()
+
+    def _t2_children(self):
+        return (self.encoder, self.decoder, self.postnet, self.decoder.prenet)
 
     def parse_batch(self, batch):
         """model.py:473-485."""

@@ -186,3 +186,58 @@ def test_parse_batch_returns_the_reference_structure():
     x, y = model.parse_batch(TextMelCollate(1)(batch))
     assert len(x) == 5 and len(y) == 2 and x[3] == 9 and x[0].dtype == torch.int64 and x[2].dtype == torch.float32
     assert x[1].tolist() == [9, 4, 2] and x[4].tolist() == [3, 6, 8] and torch.equal(x[2], y[0]) and y[1].shape == (3, 8)
+
+
+def test_deepcopy_and_pickle_resolve_their_own_root():
+    """copy.deepcopy(model) / torch.save(model): the weak back-references and the engine are per-instance runtime state
+    (a copy's children used to resolve the ORIGINAL model's engine and parameters)."""
+    import copy
+    import io
+    model = t2.Tacotron2(t2.create_hparams())
+    model._t2_link()
+    assert model.decoder._t2_root() is model and model.decoder.prenet._t2_root() is model
+    clone = copy.deepcopy(model)
+    clone._t2_link()
+    for child in (clone.encoder, clone.decoder, clone.postnet, clone.decoder.prenet):
+        assert child._t2_root() is clone
+    assert model.decoder._t2_root() is model                      # the original is untouched
+    assert "_t2_engine_obj" not in clone.__dict__
+    with torch.no_grad():
+        clone.decoder.gate_layer.linear_layer.bias.fill_(3.0)
+    assert float(model.decoder.gate_layer.linear_layer.bias) != 3.0
+    buf = io.BytesIO()
+    torch.save(model, buf)                                        # used to raise "cannot pickle weakref"
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    loaded._t2_link()
+    assert loaded.decoder._t2_root() is loaded
+    assert all(torch.equal(a, b) for a, b in zip(loaded.state_dict().values(), model.state_dict().values()))
+    # a stand-alone Decoder owns its prenet
+    dec = copy.deepcopy(t2.Decoder(t2.create_hparams()))
+    dec._t2_link()
+    assert dec.prenet._t2_root() is dec
+
+
+def test_engine_cache_key_and_invalidation():
+    """The packed device copies are keyed on (generation, pointer, torch version counter, dtype); writes through .data do
+    not move the version counter, so there is a public invalidation hook, and load_state_dict calls it."""
+    from tacotron2_b200 import _engine
+    p = torch.nn.Parameter(torch.ones(4))
+    v0 = p._version
+    p.data.mul_(2.0)
+    assert p._version == v0                                       # the hazard the hook exists for
+    g0 = _engine._weights_generation[0]
+    t2.invalidate_weights()
+    assert _engine._weights_generation[0] == g0 + 1
+    eng = _engine.Engine(t2.create_hparams())
+    eng.key = ("something",)
+    eng.invalidate()
+    assert eng.key is None
+    model = t2.Tacotron2(t2.create_hparams())
+    model.__dict__["_t2_engine_obj"] = eng
+    eng.key = ("something",)
+    model.load_state_dict(model.state_dict())
+    assert eng.key is None
+    eng.key = ("something",)
+    model.decoder.invalidate_weights()                            # through a child
+    assert eng.key is None

@@ -9,7 +9,8 @@ import torch
 import tacotron2_b200 as t2
 from oracle import tacotron2_oracle as O
 from tests.common import keep_mask, rel_err, synth_state_dict
-from tests.test_oracle_golden import GRADS, check_grads_vs_fixture, grad_inputs, load, oracle_train_step
+from tests.test_oracle_golden import (GRADS, check_grads_vs_fixture, full_grad_inputs, grad_inputs, load,
+                                      oracle_train_step)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -112,6 +113,34 @@ def test_full_train_step_matches_reference_gradient_golden(name):
     print("train step %s: loss %.6f (ref %.6f), worst gradient error %.2e" % (name, float(loss), float(ref_loss), max(errs.values())))
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad
+
+
+def test_full_size_train_step_matches_reference_gradient_golden():
+    """BASELINE.json configs[2]: the teacher-forced training step at B=64, T_text=150, T_mel=800 against the gradients
+    the REFERENCE's own autograd produced at that size (tools/make_golden.py full grad64: per parameter sum / abs-sum /
+    max + 1024 sampled entries, loss, sub-sampled outputs)."""
+    g = load("full_grad_train_b64_t150_m800")
+    sd, text, tl, ol, mels, gt, m = full_grad_inputs(g)
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    post_keep = [m["qk4"][i] for i in range(4)] + [m["qk1"]]
+    with t2.dropout_masks(prenet=m["pk"], att=m["ak"], dec=m["dk"], enc=m["ek"], post=post_keep):
+        out = model((text.cuda(), tl.cuda(), mels.cuda(), int(tl.max()), ol.cuda()))
+        loss = t2.Tacotron2Loss()(out, (mels.cuda(), gt.cuda()))
+        loss.backward()
+    torch.cuda.synchronize()
+    idx = torch.from_numpy(g["frame_index"]).long()
+    e_mel = rel_err(out[0][:, :, idx], torch.from_numpy(g["mel"]))
+    e_post = rel_err(out[1][:, :, idx], torch.from_numpy(g["mel_post"]))
+    e_gate = rel_err(out[2], torch.from_numpy(g["gate"]))
+    print("full-size train step: loss %.6f (reference %.6f), mel %.2e post %.2e gate %.2e" %
+          (float(loss), float(g["loss"]), e_mel, e_post, e_gate))
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert e_mel < TOL and e_post < TOL and e_gate < TOL
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert all(v is not None for v in grads.values())
+    check_grads_vs_fixture(grads, g, TOL)
 
 
 @pytest.mark.parametrize("B,T", [(3, 21), (5, 64)])

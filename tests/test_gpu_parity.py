@@ -12,7 +12,7 @@ import tacotron2_b200 as t2
 from oracle import tacotron2_oracle as O
 from tacotron2_b200 import _capi
 from tests.common import keep_mask, rand_text, rel_err, synth_state_dict
-from tests.test_oracle_golden import INFER, forward_inputs, infer_inputs, load
+from tests.test_oracle_golden import FULL_INFER, INFER, check_full_inference, forward_inputs, infer_inputs, load
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -157,6 +157,25 @@ def test_full_size_persistent_vs_stepwise_and_oracle_prefix():
     # size-independent properties: attention rows are probability vectors, alignments non-negative
     al = outs["persistent"][3]
     assert float((al.sum(-1) - 1).abs().max()) < 1e-4 and float(al.min()) >= 0.0
+
+
+@pytest.mark.parametrize("name", FULL_INFER)
+def test_quoted_configs_match_reference_golden_every_step(name):
+    """The configurations the benchmark numbers are quoted on, ALL steps, against fixtures produced by the reference's
+    own modules (tools/make_golden.py full): B=64 / T_text=150 / 800 steps with the bench weights (BASELINE.json
+    configs[1]) and the config-5 per-GPU shape B=32 / T_text=300 / 2000 steps.  1e-3 on mel / mel_postnet / gate /
+    alignments, stop decisions (mel_lengths and every live per-step decision) bit-exact; the measured drift of the
+    split-fp16 path at the end of the autoregressive run is printed."""
+    g = load(name)
+    sd, text, keep, S = infer_inputs(g)
+    model = make_model(sd, S, _capi.IMPL_PERSISTENT)
+    with torch.no_grad(), t2.dropout_masks(prenet=keep):
+        mel, post, gate, align = model.inference(text.cuda())
+    torch.cuda.synchronize()
+    assert mel.shape[2] == S
+    errs = check_full_inference(g, mel, post, gate[:, :, 0], align, model.mel_lengths, TOL)
+    print("quoted config %s: %s (gate pre-activation margin of the fixture %.2e, max |gate| %.3f)" % (
+        name, ", ".join("%s %.2e" % kv for kv in errs.items()), float(g["gate_margin"]), float(abs(g["gate"]).max())))
 
 
 def test_philox_mode_is_deterministic_and_statistically_sane():

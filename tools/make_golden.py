@@ -116,6 +116,96 @@ def infer_case(name, B, T_text, max_steps, quantile, wseed, tseed, mseed, wscale
          mel_post=post, gate=gate, align=align, mel_lengths=lengths, gate_margin=margin)
 
 
+def ref_free_running(model, text, keep, steps):
+    """The reference's own prenet / decode modules for exactly `steps` steps, no stop test (rows are independent,
+    so the trajectory of a row does not depend on when other rows stop): (memory, mel (B,80,S), gate (B,S), align)."""
+    dec = model.decoder
+    masks = [keep[t, l].bool() for t in range(steps) for l in range(2)]
+    with torch.no_grad(), injected_dropout(ref, MaskInjector(masks)):
+        emb = model.embedding(text).transpose(1, 2)
+        memory = model.encoder.inference(emb)
+        x = dec.get_go_frame(memory)
+        dec.initialize_decoder_states(memory, mask=None)
+        mels, gates, aligns = [], [], []
+        for _ in range(steps):
+            x = dec.prenet(x)
+            mel, gate, aw = dec.decode(x)
+            mels.append(mel); gates.append(gate); aligns.append(aw)
+            x = mel
+        mel, gate, align = dec.parse_decoder_outputs(mels, gates, aligns)
+    return memory, mel, gate[:, :, 0], align
+
+
+def pick_gate(gate, S):
+    """Gate sign and bias (applied to decoder.gate_layer; the gate is not fed back, so the mel trajectory does not depend
+    on them) such that rows stop at many different steps, at least one row never fires (the run keeps all S steps) and the
+    smallest |gate pre-activation| over the live decisions -- the distance of a stop decision from flipping -- is as
+    large as possible.  Only the running maxima of a row matter (a row fires at the first step whose gate exceeds the
+    level), so the optimum is the midpoint of the widest gap between consecutive record values that satisfies the
+    constraints: exact search, no grid."""
+    best = None
+    B = gate.shape[0]
+    for sign in (1.0, -1.0):
+        g = gate.double() * sign
+        cm = torch.cummax(g, dim=1)[0]
+        rec = torch.unique(cm.flatten())                       # sorted record values of all rows
+        gaps = rec[1:] - rec[:-1]
+        for j in torch.argsort(gaps, descending=True)[:2000].tolist():
+            level = 0.5 * float(rec[j] + rec[j + 1])
+            fired = cm > level
+            never = ~fired.any(1)
+            lengths = torch.where(never, torch.full((B,), S), fired.float().argmax(1) + 1)
+            n_never = int(never.sum())
+            if n_never < 1 or n_never > B // 4 or int(lengths.min()) < 8 or len(set(lengths.tolist())) < B // 2:
+                continue
+            live = torch.arange(S)[None, :] < lengths[:, None]
+            margin = float((g - level).abs()[live].min())
+            if best is None or margin > best[0]:
+                best = (margin, sign, -level, lengths.to(torch.int32))
+            break                                              # gaps are sorted: the first feasible one is the widest
+    assert best is not None, "no gate calibration found"
+    return best
+
+
+FULL_STRIDE, FULL_TAIL, FULL_ALIGN_STRIDE = 25, 8, 100
+
+
+def full_frame_index(S):
+    return sorted(set(range(0, S, FULL_STRIDE)) | set(range(S - FULL_TAIL, S)))
+
+
+def full_infer_case(name, B, T_text, S, wseed, tseed, mseed, wscale):
+    """The configuration a number is QUOTED on (BASELINE.json configs[1] / configs[4] per GPU), all S steps through the
+    reference's own modules.  Stored: every 25th frame + the last 8 of mel / mel_postnet, all gates, all mel_lengths,
+    the alignment argmax of every step and the alignment rows of every 100th step."""
+    sd0 = synth_state_dict(wseed, gate_bias=0.0, scale=wscale)
+    text = rand_text(B, T_text, tseed)
+    keep = keep_mask((S, 2, B, 256), 0.5, mseed)
+    memory, mel, gate0, align = ref_free_running(build(sd0), text, keep, S)
+    margin, sign, bias, lengths = pick_gate(gate0, S)
+    sd = synth_state_dict(wseed, gate_bias=bias, scale=wscale, gate_sign=sign)
+    model = build(sd)
+    with torch.no_grad():
+        gate = model.decoder.gate_layer.linear_layer.bias + sign * gate0        # what the calibrated reference outputs
+        pad = torch.arange(S)[None, :] >= lengths[:, None]
+        mel_masked = mel.masked_fill(pad[:, None, :], 0.0)
+        post = (mel_masked + model.postnet(mel_masked)).masked_fill(pad[:, None, :], 0.0)
+    if B <= 8 or os.environ.get("T2_GOLDEN_VERIFY", "1") == "1":   # the calibrated model, stop test on, gives the same thing
+        r = ref_batched_inference(model, text, keep, 0.5, S)
+        assert r[6].tolist() == lengths.tolist(), (r[6].tolist(), lengths.tolist())
+        assert torch.equal(r[1], mel) and torch.equal(r[3], post) and torch.allclose(r[4][:, :, 0], gate, atol=1e-6)
+        gate = r[4][:, :, 0]
+    idx = torch.tensor(full_frame_index(S))
+    aidx = torch.arange(0, S, FULL_ALIGN_STRIDE)
+    print(name, "lengths min/max", int(lengths.min()), int(lengths.max()), "distinct", len(set(lengths.tolist())),
+          "gate pre-activation margin %.3e" % margin)
+    save(name, B=B, T_text=T_text, max_steps=S, wseed=wseed, wscale=wscale, tseed=tseed, mseed=mseed, gate_bias=bias,
+         gate_sign=sign, wsum=weights_checksum(sd), frame_index=idx, align_index=aidx, mel_masked=mel_masked[:, :, idx],
+         mel_raw=mel[:, :, idx], mel_post=post[:, :, idx], gate=gate, mel_lengths=lengths, gate_margin=margin,
+         align_argmax=align.argmax(-1).to(torch.int16), align_max=align.max(-1)[0], align_rows=align[:, aidx],
+         memory_abs_sum=memory.double().abs().sum())
+
+
 def forward_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
     sd = synth_state_dict(wseed, scale=wscale)
     g = torch.Generator().manual_seed(seed)
@@ -168,7 +258,7 @@ def gate_targets(ol, T_mel):
     return gt
 
 
-def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
+def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0, n_samples=96, keep_outputs=True):
     """Full training step of the REFERENCE (forward + Tacotron2Loss + backward, autograd) with injected dropout
     masks; the fixture keeps the loss and, per parameter, sum / abs-sum / max of the gradient plus 96 sampled entries."""
     import importlib.util
@@ -206,16 +296,30 @@ def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0):
     loss.backward()
     arrays = dict(training=int(training), B=B, T_text=T_text, T_mel=T_mel, wseed=wseed, seed=seed, wscale=wscale,
                   wsum=weights_checksum(sd), text_lengths=tl, output_lengths=ol, mels_in=mels, gate_target=gt,
-                  loss=loss.detach(), mel=out[0].detach(), mel_post=out[1].detach())
+                  loss=loss.detach(), mel=out[0].detach(), mel_post=out[1].detach(), n_samples=n_samples)
+    if not keep_outputs:      # full-size case: the inputs are regenerated from the seeds, outputs sub-sampled in time
+        idx = torch.tensor(full_frame_index(T_mel))
+        arrays.update(mel=out[0].detach()[:, :, idx], mel_post=out[1].detach()[:, :, idx], frame_index=idx, gate=out[2].detach())
+        del arrays["mels_in"], arrays["gate_target"]
     for k, p_ in model.named_parameters():
         gr = p_.grad.detach().double().reshape(-1)
-        idx = grad_sample_index(k, gr.numel())
+        idx = grad_sample_index(k, gr.numel(), n_samples)
         arrays["g/" + k] = torch.cat((torch.stack((gr.sum(), gr.abs().sum(), gr.abs().max())), gr[idx]))
     print(name, "loss", float(loss))
     save(name, **arrays)
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":        # the configurations the benchmark numbers are quoted on
+        which = sys.argv[2:] or ["infer64", "infer32", "grad64"]
+        if "infer64" in which:   # BASELINE.json configs[1]: B=64, T_text=150, 800 steps, the bench weights (scale 1.0)
+            full_infer_case("full_infer_b64_t150_s800", 64, 150, 800, 1234, 101, 102, 1.0)
+        if "infer32" in which:   # configs[4] per GPU: B=32, T_text=300, 2000 steps
+            full_infer_case("full_infer_b32_t300_s2000", 32, 300, 2000, 1234, 111, 112, 1.0)
+        if "grad64" in which:    # configs[2]: teacher-forced training step B=64, T_mel=800
+            grad_case("full_grad_train_b64_t150_m800", True, 64, 150, 800, 1234, 160, wscale=1.0, n_samples=1024,
+                      keep_outputs=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         grad_case("grad_train_b4", True, 4, 24, 12, 1234, 60)
         grad_case("grad_eval_b3", False, 3, 17, 9, 77, 70)
