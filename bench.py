@@ -31,11 +31,20 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, T_TEXT, T_MEL = 64, 150, 800
 FLOP_PER_FRAME = 2 * (18167296 + 6720 * T_TEXT)          # 38,350,592 @ T_enc=150
 STREAM_BYTES_PER_STEP = 97.3e6                           # fp32 weights + memory + processed memory
+WORKLOAD = ("Tacotron2.inference: B=64 per GPU, T_text=150, 800 decoder frames per row (gate_threshold=1.0, "
+            "max_decoder_steps=800), encoder + decoder + postnet; BASELINE.json configs[1]")
 
 
 def synth_weights(seed=1234):
     from tests.common import synth_state_dict
     return synth_state_dict(seed, gate_bias=0.0, scale=1.0)
+
+
+def load_max_mhz():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        return 1965.0
 
 
 def load_peaks():
@@ -78,6 +87,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def host_threads():
+    """Threads this process may actually run on (the affinity mask, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _best_threads(fn, candidates):
     """Runs fn() under each thread count and returns (best_seconds, best_threads)."""
     best = None
@@ -92,77 +109,280 @@ def _best_threads(fn, candidates):
     return best
 
 
-def cpu_port_sample(threads, dec_steps=60):
-    """Times the oracle port (the reference's algorithm in plain torch CPU ops) on the host cores on a
-    bounded sample of the SAME workload: encoder + `dec_steps` of the 800 decoder steps + postnet at B=64,
-    T_text=150; the decoder part is extrapolated linearly to 800 steps (every step does identical work).
-    Each component runs at the thread count (<= all host threads) that is fastest for it -- small
-    recurrent GEMMs are slower with 100+ threads than with 16."""
-    from oracle import tacotron2_oracle as O
-    from tests.common import keep_mask, rand_text
-    cands = sorted({t for t in (8, 16, 32, 64, threads) if t <= threads})
-    sd = synth_weights()
-    text = rand_text(B_PER_GPU, T_TEXT, 1)
-    keep = keep_mask((dec_steps + 3, 2, B_PER_GPU, 256), 0.5, 2)
-    with torch.no_grad():
-        emb = sd["embedding.weight"][text].transpose(1, 2)
-        # encoder: tune on a 1/5 slice of the sequence, then time the full one
-        _, th_enc = _best_threads(lambda: O.encoder(sd, emb[:, :, :30]), cands)
-        torch.set_num_threads(th_enc)
-        t0 = time.perf_counter()
-        memory = O.encoder(sd, emb)
-        t_enc = time.perf_counter() - t0
-        st0 = O.init_decoder_state(sd, memory)
+class CpuPort:
+    """The oracle port (the reference's algorithm in plain torch CPU ops, oracle/tacotron2_oracle.py) on the host
+    cores, on the SAME workload as the GPU arm: encoder + 800 decoder steps + postnet at B=64, T_text=150.  The thread
+    count of each component (<= the affinity mask; small recurrent GEMMs are slower with 100+ threads than with 16) is
+    tuned ONCE on small slices; a pass then either runs all 800 decoder steps or, when `dec_steps` < 800, that many
+    steps extrapolated linearly (every step does identical work) -- the sample size is stated in the result."""
 
-        def steps(n, st=None):
-            st = st or {k: v.clone() for k, v in st0.items()}
-            x = memory.new_zeros(B_PER_GPU, 80)
-            ts = []
-            for t in range(n):
-                t0 = time.perf_counter()
-                px = O.prenet(sd, x, keep[t, 0], keep[t, 1])
-                x, _, _ = O.decode_step(sd, st, memory, px)
-                ts.append(time.perf_counter() - t0)
-            return ts
-        _, th_dec = _best_threads(lambda: steps(6), cands)
-        torch.set_num_threads(th_dec)
-        times = sorted(steps(dec_steps + 3)[3:])
-        step = times[len(times) // 2]
-        mel = torch.randn(B_PER_GPU, 80, T_MEL)
-        _, th_post = _best_threads(lambda: O.postnet(sd, mel[:, :, :100]), cands)
-        torch.set_num_threads(th_post)
-        t0 = time.perf_counter()
-        O.postnet(sd, mel)
-        t_post = time.perf_counter() - t0
-    total = t_enc + T_MEL * step + t_post
-    # cores = the threads actually used (the largest per-component choice; more threads made every component slower)
-    return {"value": B_PER_GPU * T_MEL / total, "unit": "mel frames/s", "cores": max(th_enc, th_dec, th_post), "kind": "port",
-            "sample": "oracle port, B=64 T_text=150, fp32, %d host threads available: encoder %.3f s (%d thr) + median of "
-                      "%d decoder steps %.1f us/step x800 (%d thr) + postnet T_mel=800 %.3f s (%d thr)"
-                      % (threads, t_enc, th_enc, dec_steps, step * 1e6, th_dec, t_post, th_post),
-            "decoder_step_us": step * 1e6}, total
+    def __init__(self):
+        from oracle import tacotron2_oracle as O
+        from tests.common import keep_mask, rand_text
+        self.O = O
+        self.threads = host_threads()
+        cands = sorted({t for t in (8, 16, 32, 64, self.threads) if t <= self.threads})
+        self.sd = synth_weights()
+        text = rand_text(B_PER_GPU, T_TEXT, 1)
+        self.keep = keep_mask((T_MEL, 2, B_PER_GPU, 256), 0.5, 2)
+        self.mel = torch.randn(B_PER_GPU, 80, T_MEL)
+        with torch.no_grad():
+            self.emb = self.sd["embedding.weight"][text].transpose(1, 2)
+            _, self.th_enc = _best_threads(lambda: O.encoder(self.sd, self.emb[:, :, :30]), cands)
+            torch.set_num_threads(self.th_enc)
+            self.memory = O.encoder(self.sd, self.emb)
+            self.st0 = O.init_decoder_state(self.sd, self.memory)
+            _, self.th_dec = _best_threads(lambda: self._steps(6), cands)
+            _, self.th_post = _best_threads(lambda: O.postnet(self.sd, self.mel[:, :, :100]), cands)
+
+    def _steps(self, n):
+        O, sd = self.O, self.sd
+        st = {k: v.clone() for k, v in self.st0.items()}
+        x = self.memory.new_zeros(B_PER_GPU, 80)
+        ts = []
+        for t in range(n):
+            t0 = time.perf_counter()
+            px = O.prenet(sd, x, self.keep[t, 0], self.keep[t, 1])
+            x, _, _ = O.decode_step(sd, st, self.memory, px)
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    def run(self, dec_steps=T_MEL):
+        """One pass; returns (cpu_baseline dict, seconds for the whole 51,200-frame workload)."""
+        O, sd = self.O, self.sd
+        dec_steps = min(int(dec_steps), T_MEL)
+        with torch.no_grad():
+            torch.set_num_threads(self.th_enc)
+            t0 = time.perf_counter()
+            O.encoder(sd, self.emb)
+            t_enc = time.perf_counter() - t0
+            torch.set_num_threads(self.th_dec)
+            ts = self._steps(dec_steps)
+            if dec_steps == T_MEL:
+                t_dec, how = sum(ts), "all 800 decoder steps measured"
+            else:
+                body = sorted(ts[min(3, dec_steps // 4):])
+                t_dec = T_MEL * body[len(body) // 2]
+                how = "median of %d decoder steps x 800 (extrapolated)" % dec_steps
+            torch.set_num_threads(self.th_post)
+            t0 = time.perf_counter()
+            O.postnet(sd, self.mel)
+            t_post = time.perf_counter() - t0
+        total = t_enc + t_dec + t_post
+        return {"value": B_PER_GPU * T_MEL / total, "unit": "mel frames/s", "cores": max(self.th_enc, self.th_dec, self.th_post),
+                "kind": "port",
+                "sample": "oracle port, B=64 T_text=150, fp32, %d host threads usable: encoder %.3f s (%d thr) + decoder %.3f s "
+                          "(%s, %d thr) + postnet T_mel=800 %.3f s (%d thr)"
+                          % (self.threads, t_enc, self.th_enc, t_dec, how, self.th_dec, t_post, self.th_post),
+                "decoder_step_us": t_dec / T_MEL * 1e6, "decoder_steps_measured": dec_steps}, total
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's algorithm on the host cores (the oracle port: the reference is pure Python and
+    /root/reference does not exist on the GPU box), same metric / config as the GPU arm.  The first warm-up pass runs the
+    complete workload; if K such passes would not fit ~4 minutes the timed passes measure a bounded number of decoder steps
+    and extrapolate (stated in config.workload)."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    vals = []
-    for i in range(args.warmup + args.steps):
-        cb, total = cpu_port_sample(threads, dec_steps=20 if i < args.warmup else 40)
-        if i >= args.warmup:
-            vals.append((cb, total))
+    t_start = time.perf_counter()
+    port = CpuPort()
+    cb, full_s = port.run(T_MEL)                      # warm-up pass 1: the whole workload, nothing extrapolated
+    for _ in range(max(args.warmup - 1, 0)):
+        port.run(40)
+    budget = 240.0 - (time.perf_counter() - t_start)
+    dec_steps = T_MEL if full_s * args.steps <= budget else max(40, int(T_MEL * budget / (full_s * args.steps)) // 10 * 10)
+    vals = [port.run(dec_steps) for _ in range(args.steps)]
+    vals.sort(key=lambda v: v[1])
     cb = vals[len(vals) // 2][0]
     ms = sum(v[1] for v in vals) / len(vals) * 1e3
+    cb["full_pass_s"] = full_s
     line = {"impl": "reference", "metric": "mel frames/sec (B=64,T_text=150)", "value": cb["value"], "unit": "mel frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Tacotron2.inference B=64 T_text=150 T_mel=800 (BASELINE.json configs[1]) on host CPU cores; "
-                                   "each step = bounded sample extrapolated to 800 decoder steps"},
+            "config": {"workload": WORKLOAD + "; reference arm: oracle port on the host CPU cores, %s per timed pass"
+                                   % ("all 800 decoder steps" if dec_steps == T_MEL else
+                                      "%d of 800 decoder steps measured, extrapolated linearly" % dec_steps),
+                       "global_batch": B_PER_GPU},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
     print(json.dumps(line))
+
+
+def decoder_traffic():
+    """DRAM bytes per decoder step of the persistent kernel from the committed ncu capture (profiles/decoder_traffic.json,
+    written by tools/ncu_summary.py) -- valid only for the kernel source it was captured from: a stale hash gives None."""
+    import hashlib
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json")))
+        src = open(os.path.join(ROOT, "tacotron2_b200", "csrc", "decoder_persistent.cu"), "rb").read()
+        if hashlib.sha256(src).hexdigest()[:16] != d.get("source_sha16"):
+            return None, "profiles/decoder_traffic.json is stale (kernel source changed since the capture)"
+        return float(d["dram_bytes_per_step"]), d.get("capture")
+    except Exception as e:
+        return None, "unavailable: %s" % str(e)[:80]
+
+
+def train_inputs(B, Tt, Tm, seed):
+    """sorted text lengths U[Tt/2, Tt] (max = Tt), mel ~ N(0,1), output lengths
+    U[Tm/2, Tm] (max = Tm), zero-padded targets, gate target 1 from the last frame on (data_utils.py:97-107)."""
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(0, 148, (B, Tt), generator=g)
+    tl = torch.sort(torch.randint(Tt // 2, Tt + 1, (B,), generator=g), descending=True)[0]
+    tl[0] = Tt
+    ol = torch.randint(Tm // 2, Tm + 1, (B,), generator=g)
+    ol[0] = Tm
+    mels = torch.randn(B, 80, Tm, generator=g)
+    gt = torch.zeros(B, Tm)
+    for i, n in enumerate(ol.tolist()):
+        mels[i, :, n:] = 0
+        gt[i, n - 1:] = 1
+    return text, tl, mels, gt, ol
+
+
+def train_block(t2, hp, rank, world, iters=3, warmup=2):
+    """BASELINE.json configs[2] / configs[3], measured AFTER the headline region: one teacher-forced training step
+    (Tacotron2.forward + Tacotron2Loss + backward + clip + Adam, train.py:209-236) at B=64 per GPU, T_text=150,
+    T_mel=800; with N > 1 the same step under apply_gradient_allreduce (bucketed NCCL all-reduce launched from the
+    backward hooks, distributed.py:126-173).  Times are CUDA events, max over ranks.  exposed all-reduce = DP step -
+    local step on the same ranks."""
+    import torch.distributed as dist
+    from tacotron2_b200.distributed import apply_gradient_allreduce
+    torch.manual_seed(1234)
+    model = t2.Tacotron2(hp)
+    model.load_state_dict(synth_weights())
+    model = model.cuda().train()
+    opt = t2.FusedClipAdam(model.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+    crit = t2.Tacotron2Loss()
+    text, tl, mels, gt, ol = (x.cuda() for x in train_inputs(B_PER_GPU, T_TEXT, T_MEL, 1234 + rank))
+    x = (text, tl, mels, int(tl.max()), ol)
+
+    def one_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        model.zero_grad(set_to_none=True)
+        out = model(x)
+        loss = crit(out, (mels, gt))
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        opt.step(max_norm=hp.grad_clip_thresh)
+        ev[3].record()
+        ev[3].synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)], float(loss)
+
+    def timed_steps():
+        for _ in range(warmup):
+            one_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        rows = [one_step() for _ in range(iters)]
+        t = torch.tensor([sum(r[0][k] for r in rows) / iters for k in range(3)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()], rows[-1][1]
+
+    L = _launch_counter()
+    l0 = L()
+    local, loss = timed_steps()
+    launches = (L() - l0) // (iters + warmup)
+    n_param = sum(p.numel() for p in model.parameters())
+    out = {"workload": "teacher-forced training step B=64 per GPU, T_text=150, T_mel=800, fp32-grade (split-fp16 tensor-core "
+                       "operands), fwd + loss + bwd + clip + Adam; BASELINE.json configs[2]",
+           "ms_per_step": sum(local), "forward_loss_ms": local[0], "backward_ms": local[1], "clip_adam_ms": local[2],
+           "frames_per_s": B_PER_GPU * T_MEL * world / (sum(local) * 1e-3) if world == 1 else None,
+           "loss": loss, "gpu_launches_per_step": int(launches), "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if world > 1:
+        apply_gradient_allreduce(model)
+        dp, _ = timed_steps()
+        out.update({"workload": out["workload"].replace("configs[2]", "configs[3]: data parallel, NCCL gradient all-reduce"),
+                    "local_ms_per_step": sum(local), "ms_per_step": sum(dp), "forward_loss_ms": dp[0], "backward_ms": dp[1],
+                    "clip_adam_ms": dp[2], "allreduce_exposed_ms": sum(dp) - sum(local),
+                    "allreduce_bytes": n_param * 4, "frames_per_s": B_PER_GPU * T_MEL * world / (sum(dp) * 1e-3),
+                    "dp_efficiency_vs_local_step": sum(local) / sum(dp)})
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def config5_block(t2, hp, rank, world, iters=2):
+    """BASELINE.json configs[4]: long-sequence inference B=256 over 8 GPUs = 32 rows per GPU, T_text=300, 2000 decoder
+    steps (gate_threshold = 1.0); per-GPU share measured on every rank, max over ranks."""
+    import contextlib
+    import torch.distributed as dist
+    from tests.common import rand_text
+    model = t2.Tacotron2(hp)
+    model.load_state_dict(synth_weights())
+    model = model.cuda().eval()
+    model.decoder.max_decoder_steps, model.decoder.gate_threshold = 2000, 1.0
+    text = rand_text(32, 300, 200 + rank).cuda()
+    ms = []
+    for it in range(iters + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
+            out = model.inference(text)
+        e1.record()
+        e1.synchronize()
+        if it:
+            ms.append(e0.elapsed_time(e1))
+    assert out[0].shape == (32, 80, 2000)
+    t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    m = float(t.cpu())
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": "Tacotron2.inference B=32 per GPU, T_text=300, 2000 decoder frames per row; BASELINE.json configs[4] "
+                        "(B=256 over 8 GPUs)", "ms_per_batch": m, "frames_per_s": 32 * 2000 * world / (m * 1e-3),
+            "decoder_step_us": None}
+
+
+def eager_gpu_context():
+    """Context only: the oracle port -- plain torch ops, what stock PyTorch eager does with this model --
+    on cuda:0, outside every timed region of the GPU arm: encoder + 60 decoder steps (extrapolated to 800) + postnet."""
+    try:
+        from oracle import tacotron2_oracle as O
+        from tests.common import keep_mask, rand_text
+        sd = {k: v.cuda() for k, v in synth_weights().items()}
+        text = rand_text(B_PER_GPU, T_TEXT, 1).cuda()
+        keep = keep_mask((64, 2, B_PER_GPU, 256), 0.5, 2).cuda()
+        with torch.no_grad():
+            emb = sd["embedding.weight"][text].transpose(1, 2)
+            memory = O.encoder(sd, emb)
+            mel = torch.randn(B_PER_GPU, 80, T_MEL, device="cuda")
+            res = {}
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                memory = O.encoder(sd, emb)
+                torch.cuda.synchronize()
+                t_enc = time.perf_counter() - t0
+                st = O.init_decoder_state(sd, memory)
+                x = memory.new_zeros(B_PER_GPU, 80)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for t in range(60):
+                    px = O.prenet(sd, x, keep[t, 0], keep[t, 1])
+                    x, _, _ = O.decode_step(sd, st, memory, px)
+                torch.cuda.synchronize()
+                t_step = (time.perf_counter() - t0) / 60
+                t0 = time.perf_counter()
+                O.postnet(sd, mel)
+                torch.cuda.synchronize()
+                t_post = time.perf_counter() - t0
+                res = {"frames_per_s": B_PER_GPU * T_MEL / (t_enc + T_MEL * t_step + t_post), "decoder_step_us": t_step * 1e6,
+                       "encoder_ms": t_enc * 1e3, "postnet_ms": t_post * 1e3,
+                       "what": "oracle port (plain torch fp32 ops, TF32 off) on cuda:0, 60 decoder steps extrapolated to 800; context only"}
+        return res
+    except Exception as e:
+        return {"unavailable": str(e)[:120]}
+
+
+def _launch_counter():
+    from tacotron2_b200 import _capi
+    return _capi.lib().t2_kernel_launch_count
 
 
 def main():
@@ -173,6 +393,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--decoder-impl", default="auto", choices=["auto", "stepwise", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the train / config5 / eager_gpu blocks (A/B runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -263,11 +484,18 @@ def main():
     try:
         prof = eng.decoder_profile()
         tot = sum(v[0] for v in prof.values()) or 1
-        phase_profile = {k: {"us_per_step_cta0_60_100": [round(x / 1965.0 / T_MEL, 2) for x in v]} for k, v in prof.items()}
+        sm_mhz = float((sampler.summary().get("sm_mhz") or 0) or load_max_mhz())     # clock64 ticks at the SM clock
+        phase_profile = {k: {"us_per_step_cta0_60_100": [round(x / sm_mhz / T_MEL, 2) for x in v]} for k, v in prof.items()}
+        phase_profile["sm_mhz_used"] = sm_mhz
     except Exception as e:  # stepwise implementation has no phase profile
         phase_profile = {"unavailable": str(e)[:80]}
     n_frames = int(out_host[2][0]) * B_PER_GPU
     assert n_frames == B_PER_GPU * T_MEL, "workload did not produce 800 frames per row: %d" % n_frames
+    extras = None
+    if not args.no_extras:       # after (and outside) the headline region; every rank takes part (DP all-reduce at N > 1)
+        del flush
+        torch.cuda.empty_cache()
+        extras = {"train": train_block(t2, hp, rank, world), "config5": config5_block(t2, hp, rank, world)}
     t = torch.tensor([ms_dev, ms_e2e, ms_dec], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -280,6 +508,7 @@ def main():
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     peak_tf, peak_gbs, peak_src = load_peaks()
+    traffic_step, traffic_src = decoder_traffic()
     dec_s = ms_dec * 1e-3 / args.steps
     ach_tf = B_PER_GPU * T_MEL * FLOP_PER_FRAME / dec_s / 1e12
     ach_gbs = T_MEL * STREAM_BYTES_PER_STEP / dec_s / 1e9
@@ -289,27 +518,34 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (split-fp16 tensor-core operands hi+lo, fp32 accumulate and state)", "data": "synthetic",
-        "config": {"workload": "Tacotron2.inference: B=64 per GPU, T_text=150, 800 decoder frames per row "
-                               "(gate_threshold=1.0, max_decoder_steps=800), encoder + decoder + postnet; BASELINE.json configs[1]",
+        "config": {"workload": WORKLOAD,
                    "global_batch": B_PER_GPU * world, "parallelism": "dp%d (batch sharded, no collective)" % world,
                    "l2": "256 MiB flush between timed iterations", "decoder_impl": args.decoder_impl, "device": info},
         "e2e": {"value": e2e, "unit": "mel frames/s", "h2d_bytes_per_step": B_PER_GPU * T_TEXT * 8,
-                "d2h_bytes_per_step": B_PER_GPU * 80 * T_MEL * 4 + B_PER_GPU * 4 + 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": B_PER_GPU * 80 * T_MEL * 4 + B_PER_GPU * 4 + 4, "ms_per_step": ms_e2e / args.steps,
+                "returns": "mel_outputs_postnet (B,80,800) fp32 + mel_lengths (B) + n_steps -- what the vocoder consumes; "
+                           "the reference's inference() also returns mel_outputs, gate and alignments (+51 MB), which stay on "
+                           "the device here"},
         "gpu_launches": int(launches),
         "decoder_step_us": dec_s / T_MEL * 1e6, "decoder_ms": dec_s * 1e3,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                     # dram__bytes_read+write of the persistent kernel from the ncu --set full capture in
-                     # profiles/r01_decoder_final_ncu_summary.md (3.796 GB per 100-step launch), scaled to 800 steps
-                     "traffic": 3.796e9 * T_MEL / 100, "kernel": "decoder (persistent kernel + processed_memory GEMM), CUDA events",
+                     # dram__bytes_read + write of the persistent kernel per launch, from the committed ncu --set full capture of
+                     # THIS kernel source (profiles/decoder_traffic.json; null when the source changed since)
+                     "traffic": traffic_step * T_MEL if traffic_step else None, "traffic_source": traffic_src, "kernel": "decoder (persistent kernel + processed_memory GEMM), CUDA events",
                      "peak_source": peak_src, "algorithmic_flop_per_frame": FLOP_PER_FRAME,
                      "stream_bytes": {"achieved_GBps": ach_gbs, "peak_GBps": peak_gbs, "frac": ach_gbs / peak_gbs,
                                       "bytes_per_step": STREAM_BYTES_PER_STEP}},
         "clocks": sampler.summary(),
         "decoder_phase_profile": phase_profile,
     }
+    if extras is not None:
+        line.update(extras)
     if not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_port_sample(os.cpu_count() or 1, dec_steps=60)
+        port = CpuPort()
+        port.run(20)                                     # warm-up
+        cb, _ = port.run(100)                            # bounded sample: ~10-30 s of CPU work including the tuning
         line["cpu_baseline"] = cb
+        line["eager_gpu"] = eager_gpu_context()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

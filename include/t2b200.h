@@ -256,6 +256,28 @@ typedef struct T2AdamArgs {
 size_t t2_clip_adam_workspace_bytes(int64_t total_elements, int32_t n_tensors);
 int    t2_clip_adam_step(const T2AdamArgs* a, void* stream);
 
+/* ---- mixed-precision optimizer step (the reference trains "fp16" through Apex AMP O2, train.py:173-176, 222-236) ------
+ * fp16 (or fp32) model parameters + fp32 master copies; gradients arrive in the parameter's dtype multiplied by the
+ * dynamic loss scale state[0].  One call = unscale, overflow check, clip_grad_norm_ on the unscaled gradients, Adam on
+ * the masters, write-back of the model copies, loss-scaler update (apex LossScaler: overflow -> skip the step, scale *
+ * backoff_factor; growth_interval consecutive good steps -> scale * growth_factor).  Three multi-tensor launches, no host
+ * synchronisation: `state` (4 floats on the device: loss scale, good steps since the last scale change, optimizer steps
+ * taken -- skipped steps do not count --, 1.0 if this step was skipped) carries everything between calls. */
+typedef struct T2AmpAdamArgs {
+  int32_t n;
+  void* const* model_params; const int32_t* param_is_half;   /* per tensor: storage read by the model, 1 = __half */
+  const void* const* grads;  const int32_t* grad_is_half;    /* per tensor: gradient x loss scale */
+  float* const* master; float* const* exp_avg; float* const* exp_avg_sq; const int64_t* numel;
+  double lr, beta1, beta2, eps, weight_decay, max_norm;
+  int32_t growth_interval; float growth_factor, backoff_factor;
+  float* state;            /* device, 4 floats (see above) */
+  float* grad_norm;        /* device out: norm of the unscaled gradients before clipping (inf / nan on overflow) */
+  int32_t* skipped;        /* device out (may be NULL): 1 = overflow, nothing was updated */
+  void* ws; size_t ws_bytes;
+} T2AmpAdamArgs;
+size_t t2_amp_adam_workspace_bytes(int64_t total_elements, int32_t n_tensors);
+int    t2_amp_adam_step(const T2AmpAdamArgs* a, void* stream);
+
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
  * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on
@@ -267,14 +289,23 @@ int    t2_infer_host(T2Model* m, const int64_t* text_host, int32_t B, int32_t T_
                      float* mel_post_host, int32_t* mel_lengths_host, int32_t* n_steps_host,
                      void* ws, size_t ws_bytes, void* stream);
 
-/* ---- self tests / instrumentation -------------------------------------------------------------
+/* ---- self tests (libt2b200_selftest.so only: the same sources built with -DT2_SELFTEST; not part of the product
+ * library) -------------------------------------------------------------------------------------------------
  * t2_selftest_umma: runs the tcgen05 split-fp16 GEMM engine used by the persistent decoder on a
- * (64 x K) x (N x K)^T problem and writes C (64 x N) fp32; used by tests/test_umma_gemm.py. */
+ * (64 x K) x (N x K)^T problem and writes C (64 x N) fp32. */
+#ifdef T2_SELFTEST
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes,
                      float* C, void* stream);
 /* Micro-benchmark: SM cycles for `reps` back-to-back tcgen05.mma (M x N x 16, fp16, operands resident in
  * shared memory) -> out_host[0] = issue cycles, out_host[1] = issue + completion cycles. */
 int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host);
+/* The training path's general tensor-core GEMM (gemm_tc.cu): row-major C = op(A) . op(B) + beta C, strided batch. */
+int t2_selftest_gemm_tc(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
+                        const float* B, int64_t ldb, float* C, int64_t ldc, float beta, int32_t batch,
+                        int64_t strideA, int64_t strideB, int64_t strideC, void* stream);
+int t2_selftest_colsum(const float* X, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream);
+#endif
+/* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* After a T2_IMPL_PERSISTENT run with the same args / workspace: SM cycles spent per phase of the
  * persistent kernel, summed over steps, on three sample CTAs (out_host[3][24]; phase list in
  * decoder_persistent.cu).  Synchronises the device. */

@@ -4,7 +4,8 @@ from ._engine import dropout_masks, invalidate_weights  # noqa: F401
 from .hparams import create_hparams  # noqa: F401
 from .loss_function import Tacotron2Loss  # noqa: F401
 from .model import Decoder, Encoder, Postnet, Tacotron2  # noqa: F401
-from .optim import FusedClipAdam  # noqa: F401
+from . import amp  # noqa: F401
+from .optim import AmpFusedClipAdam, FusedClipAdam  # noqa: F401
 
 __all__ = ["Tacotron2", "Encoder", "Decoder", "Postnet", "Tacotron2Loss", "create_hparams", "dropout_masks",
-           "FusedClipAdam", "invalidate_weights"]
+           "FusedClipAdam", "AmpFusedClipAdam", "amp", "invalidate_weights"]

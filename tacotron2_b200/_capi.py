@@ -16,12 +16,12 @@ EXPORTS = [
     "t2_model_destroy", "t2_encoder_workspace_bytes", "t2_encoder_forward",
     "t2_decoder_workspace_bytes", "t2_decoder_run", "t2_prenet_forward",
     "t2_postnet_workspace_bytes", "t2_postnet_forward", "t2_infer_workspace_bytes", "t2_infer_host",
-    "t2_selftest_umma", "t2_kernel_launch_count", "t2_decoder_profile", "t2_selftest_mma_rate",
+    "t2_kernel_launch_count", "t2_decoder_profile",
     "t2_decoder_stash_bytes", "t2_decoder_backward_workspace_bytes", "t2_decoder_backward",
     "t2_prenet_backward_workspace_bytes", "t2_prenet_backward",
     "t2_encoder_stash_bytes", "t2_encoder_backward_workspace_bytes", "t2_encoder_backward",
     "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
-    "t2_clip_adam_workspace_bytes", "t2_clip_adam_step",
+    "t2_clip_adam_workspace_bytes", "t2_clip_adam_step", "t2_amp_adam_workspace_bytes", "t2_amp_adam_step",
 ]
 
 
@@ -88,6 +88,18 @@ class T2AdamArgs(C.Structure):
                 ("grad_norm", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class T2AmpAdamArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("model_params", C.POINTER(C.c_void_p)), ("param_is_half", C.POINTER(C.c_int32)),
+                ("grads", C.POINTER(C.c_void_p)), ("grad_is_half", C.POINTER(C.c_int32)),
+                ("master", C.POINTER(C.c_void_p)), ("exp_avg", C.POINTER(C.c_void_p)), ("exp_avg_sq", C.POINTER(C.c_void_p)),
+                ("numel", C.POINTER(C.c_int64)),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("max_norm", C.c_double),
+                ("growth_interval", C.c_int32), ("growth_factor", C.c_float), ("backoff_factor", C.c_float),
+                ("state", C.c_void_p), ("grad_norm", C.c_void_p), ("skipped", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
@@ -139,6 +151,9 @@ def lib():
     L.t2_clip_adam_workspace_bytes.restype = C.c_size_t
     L.t2_clip_adam_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     L.t2_clip_adam_step.argtypes = [C.POINTER(T2AdamArgs), C.c_void_p]
+    L.t2_amp_adam_workspace_bytes.restype = C.c_size_t
+    L.t2_amp_adam_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.t2_amp_adam_step.argtypes = [C.POINTER(T2AmpAdamArgs), C.c_void_p]
     L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
     L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]
@@ -150,14 +165,39 @@ def lib():
     L.t2_infer_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]
-    L.t2_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_void_p, C.c_void_p]
-    L.t2_selftest_mma_rate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
     L.t2_decoder_profile.argtypes = [C.POINTER(T2DecoderArgs), C.POINTER(C.c_int64)]
     if L.t2_abi_version() != 1:
         raise RuntimeError("libt2b200.so ABI version mismatch")
     _lib = L
     return L
+
+
+SELFTEST_LIB_PATH = os.path.join(_HERE, "libt2b200_selftest.so")
+SELFTEST_EXPORTS = ["t2_selftest_umma", "t2_selftest_mma_rate", "t2_selftest_gemm_tc", "t2_selftest_colsum"]
+_selftest_lib = None
+
+
+def selftest_lib():
+    """libt2b200_selftest.so: the product sources built with -DT2_SELFTEST (adds t2_selftest_*); tests / tools only."""
+    global _selftest_lib
+    if _selftest_lib is None:
+        if not os.path.isfile(SELFTEST_LIB_PATH):
+            raise RuntimeError("tacotron2_b200: %s is missing -- run `make -C tacotron2_b200/csrc`" % SELFTEST_LIB_PATH)
+        L = C.CDLL(SELFTEST_LIB_PATH)
+        L.t2_last_error.restype = C.c_char_p
+        L.t2_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.t2_selftest_mma_rate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        L.t2_selftest_gemm_tc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int64,
+                                          C.c_int64, C.c_int64, C.c_void_p]
+        L.t2_selftest_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        _selftest_lib = L
+    return _selftest_lib
+
+
+def check_selftest(rc):
+    if rc != 0:
+        raise T2Error("libt2b200_selftest error %d: %s" % (rc, selftest_lib().t2_last_error().decode()))
 
 
 class T2Error(RuntimeError):

@@ -6,6 +6,7 @@
 
 #include "conv_tc.h"
 #include "decoder.h"
+#include "gemm_tc.h"
 #include "gemm_f32.cuh"
 #include "train_layers.h"
 
@@ -239,6 +240,7 @@ int t2_model_destroy(T2Model* m) {
   for (int i = 0; i < 5; ++i) cudaFree(m->tc_post_conv[i]);
   cudaFree(m->tc_enc_wih);
   persistent_pack_destroy(m);
+  gemm_tc_destroy(m);
   blas_destroy(m);
   delete m;
   return T2_OK;
@@ -388,6 +390,7 @@ int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host) {
   return T2_OK;
 }
 
+#ifdef T2_SELFTEST   // libt2b200_selftest.so only
 int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host) {
   return mma_rate(M, N, reps, alternate_d, (long long*)out_host, 0);
 }
@@ -395,5 +398,21 @@ int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes, float* C, void* stream) {
   return selftest_umma(A, W, N, K, passes, C, (cudaStream_t)stream);
 }
+
+// C = op(A) . op(B) + beta C through the training path's tensor-core GEMM (gemm_tc.cu); batch > 1: strided batch
+int t2_selftest_gemm_tc(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
+                        int64_t ldb, float* C, int64_t ldc, float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                        int64_t strideC, void* stream) {
+  static T2Model scratch_owner;            // only its GEMM scratch is used
+  GemmTc g;
+  g.ta = ta != 0; g.tb = tb != 0; g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.beta = beta; g.batch = batch; g.strideA = strideA; g.strideB = strideB; g.strideC = strideC;
+  return gemm_tc(&scratch_owner, (cudaStream_t)stream, g);
+}
+int t2_selftest_colsum(const float* X, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream) {
+  static T2Model scratch_owner;
+  return colsum_f32(&scratch_owner, (cudaStream_t)stream, X, ld, rows, cols, out);
+}
+#endif
 
 }  // extern "C"

@@ -15,6 +15,8 @@ struct DecoderCtrl {
   int pad2_[2];
   int done[kMaxBatch];     // per-row stop latch
   long long prof[3][24];   // cycles per phase of the persistent kernel, sampled on CTAs 0 / 60 / 100
+  unsigned int x1_count; int pad3_[31];    // arrivals of the projection CTAs: x1 (and the stop flag) of step t written
+  unsigned int x2_count; int pad4_[31];    // arrivals of the prenet-2 CTAs: x2 of step t + 1 written
 };
 
 struct DecoderWs {

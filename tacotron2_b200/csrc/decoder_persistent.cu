@@ -45,7 +45,8 @@ namespace {
 constexpr int kG = 128;               // CTAs
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 4;
+constexpr int kStages = 4;             // ring stages of the helper kernels (self test, backward GEMMs)
+constexpr int kMaxStages = 5;          // the decoder kernel takes 5 when shared memory allows (T_enc <~ 330), else 4
 constexpr int kRows = 64;             // batch rows per launch (zero padded)
 constexpr int kXChunkBytes = 2 * kRows * kChunkK * 2;    // [hi 64 rows | lo 64 rows] x 64 k fp16 = 16 KiB
 // accumulator columns: each consumer owns [hi-part n | lo-part n]: att 0-63, dec 64-127, shared slot 128-159
@@ -70,6 +71,7 @@ struct EventPlan {
   int32_t col0;         // accumulator column of the first consumer
   int32_t ncons;
   int32_t n[3];         // rows per consumer (packing only)
+  int32_t chunks;       // K chunks of this event (bounds the weight prefetch)
 };
 struct CtaPlan {
   EventPlan ev[kNumEvents];
@@ -210,6 +212,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Decode
   }
 }
 
+// One thread of a CTA publishes the CTA's stores (ordered before it by __syncthreads) and bumps a counter: a single
+// gpu-scope fence followed by a relaxed reduction (fence + relaxed atomic = release; __threadfence() followed by
+// red.release paid for two fences).  The waiting side polls with relaxed loads and fences once after the value
+// arrived (an acquire load per poll iteration costs a fence per iteration).
+__device__ __forceinline__ void arrive_release(unsigned int* cnt) {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+}
+__device__ __forceinline__ void poll_acquire(unsigned int* cnt, unsigned int target, DecoderCtrl* ctrl, int code) {
+  const unsigned long long t0 = clock64();
+  while (true) {
+    unsigned int c;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt) : "memory");
+    if ((int)(c - target) >= 0) break;
+    if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, code);
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 // grid-wide barrier: one monotonically increasing arrival counter; arrive = red.release, wait = poll with
 // ld.acquire until the counter reaches this barrier's target (no reset / generation hop).  Also orders
 // the generic-proxy stores of the epilogues before the async-proxy (bulk copy) reads of the next event.
@@ -239,15 +260,8 @@ __device__ __forceinline__ void grid_barrier(DecoderCtrl* ctrl, unsigned int& ta
   __syncthreads();
   target += gridDim.x;
   if (threadIdx.x == 0) {
-    __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
-    const unsigned long long t0 = clock64();
-    while (true) {
-      unsigned int c;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->bar_count) : "memory");
-      if ((int)(c - target) >= 0) break;
-      if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 100);
-    }
+    arrive_release(&ctrl->bar_count);
+    poll_acquire(&ctrl->bar_count, target, ctrl, 100);
   }
   __syncthreads();
   ptx::fence_proxy_async();
@@ -260,22 +274,44 @@ __device__ __forceinline__ void grid_arrive(DecoderCtrl* ctrl, unsigned int& tar
   __syncthreads();
   target += gridDim.x;
   if (threadIdx.x == 0) {
-    __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->bar_count) : "memory");
+    arrive_release(&ctrl->bar_count);
   }
 }
 __device__ __forceinline__ void grid_wait(DecoderCtrl* ctrl, unsigned int target) {
   if (threadIdx.x == 0) {
-    const unsigned long long t0 = clock64();
-    while (true) {
-      unsigned int c;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(&ctrl->bar_count) : "memory");
-      if ((int)(c - target) >= 0) break;
-      if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 101);
-    }
+    poll_acquire(&ctrl->bar_count, target, ctrl, 101);
   }
   __syncthreads();
   ptx::fence_proxy_async();
+}
+
+// producer-scoped hand-over: the producers of a block signal a monotonic counter once their stores are done, the
+// consumers wait until it reaches (#producers x step).  Same fences as the grid barrier on both sides.
+constexpr unsigned int kStopFlag = 1u << 24;    // counters count arrivals in bits 0-23 (32 x 524k steps), bits 24+ = "stop"
+__device__ __forceinline__ void signal_counter(unsigned int* cnt, unsigned int inc) {
+  ptx::fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(inc) : "memory");
+  }
+}
+// returns true when a producer attached the stop flag
+__device__ __forceinline__ bool wait_counter(unsigned int* cnt, unsigned int target, int* s_flag, DecoderCtrl* ctrl, int code) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = clock64();
+    unsigned int c;
+    while (true) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt) : "memory");
+      if ((c & (kStopFlag - 1u)) >= target) break;
+      if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, code);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    *s_flag = (int)(c >> 24);
+  }
+  __syncthreads();
+  ptx::fence_proxy_async();
+  return *s_flag != 0;
 }
 
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
@@ -304,6 +340,7 @@ struct Ring {
   uint64_t pol_x, pol_w;       // L2 eviction policies of the activation / weight streams
   uint32_t cs, rank;           // cluster size (1 = no multicast) and this CTA's rank in it
   uint32_t pre;                // stages whose weight chunk was already issued for the upcoming event
+  uint32_t ns;                 // number of stages
 };
 
 // Weight chunks do not depend on the grid barrier that separates two events (only the activation does):
@@ -312,14 +349,15 @@ struct Ring {
 __device__ __forceinline__ void prefetch_weights(Ring& rg, const EventPlan& nx, const uint8_t* w_img,
                                                  DecoderCtrl* ctrl) {
   uint32_t s = rg.p_stage, ph = rg.p_phase;
-  for (int i = 0; i < kStages; ++i) {
+  const uint32_t n = min(rg.ns, (uint32_t)nx.chunks);
+  for (uint32_t i = 0; i < n; ++i) {
     mbar_wait(&rg.empty[s], ph ^ 1, ctrl, 205);
     ptx::mbar_arrive_expect_tx(&rg.full[s], kXChunkBytes + nx.w_bytes);
     ptx::bulk_g2s_hint(rg.stage(s) + kXChunkBytes, w_img + nx.w_off + (size_t)i * nx.w_bytes, nx.w_bytes,
                        &rg.full[s], rg.pol_w);
-    if (++s == kStages) { s = 0; ph ^= 1; }
+    if (++s == rg.ns) { s = 0; ph ^= 1; }
   }
-  rg.pre = kStages;
+  rg.pre = n;
 }
 
 // Streams `chunks` K-chunks of the activation image x_img plus this CTA's weight rows through the ring
@@ -350,7 +388,7 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
           ptx::bulk_g2s_mc_hint(st + rg.rank * slice, x_img + (size_t)i * kXChunkBytes + rg.rank * slice, slice,
                                 &rg.full[rg.p_stage], (uint16_t)((1u << rg.cs) - 1u), rg.pol_x);
         }
-        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
+        if (++rg.p_stage == rg.ns) { rg.p_stage = 0; rg.p_phase ^= 1; }
       }
       rg.pre = 0;
       if (next != nullptr && next->nrows != 0) prefetch_weights(rg, *next, w_img, ctrl);
@@ -373,7 +411,7 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
         }
         if (rg.cs == 1) ptx::umma_commit(&rg.empty[rg.c_stage]);   // frees the stage once these MMAs have read it
         else ptx::umma_commit_mc(&rg.empty[rg.c_stage], (uint16_t)((1u << rg.cs) - 1u));
-        if (++rg.c_stage == kStages) { rg.c_stage = 0; rg.c_phase ^= 1; }
+        if (++rg.c_stage == rg.ns) { rg.c_stage = 0; rg.c_phase ^= 1; }
       }
       ptx::umma_commit(rg.acc);
     }
@@ -443,6 +481,7 @@ struct KParams {
   float* mel; float* gate; float* align; int32_t* mel_lengths; int32_t* n_steps;
   DecoderCtrl* ctrl;
   int B, T, cap, infer, training, cluster, hier_barrier;
+  int nstages;                      // operand ring stages (4 or 5)
   int b0, Btot;                     // this launch handles batch rows [b0, b0 + B) of Btot (dropout mask / Philox indexing)
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
@@ -475,33 +514,39 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   // ---- shared memory carve-up ----
   uint8_t* sp = smem_raw;
   Ring rg;
-  rg.stage0 = sp; sp += kStages * kStageBytes;
+  rg.ns = (uint32_t)p.nstages;
+  rg.stage0 = sp; sp += p.nstages * kStageBytes;
   uint8_t* s_weff = sp; sp += kWeffBytes;                                     // fused location filter image
   uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 16 * sizeof(uint64_t);
-  rg.full = bars; rg.empty = bars + kStages; rg.acc = bars + 2 * kStages;
+  rg.full = bars; rg.empty = bars + kMaxStages; rg.acc = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp); sp += 16;
   int* s_live = reinterpret_cast<int*>(sp); sp += 16;
+  int* s_flag = s_live + 1;                                                    // stop flag broadcast of wait_counter
   float* s_bias_a = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_bias_d = reinterpret_cast<float*>(sp); sp += 32 * 4;
   float* s_v = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_q = reinterpret_cast<float*>(sp); sp += kAtt * 4;
   float* s_red = reinterpret_cast<float*>(sp); sp += 32 * 4;
-  float* s_xch = reinterpret_cast<float*>(sp); sp += kRows * kXchStride * 4;  // lo-row halves of the accumulators
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(sp); sp += kRows * 4;        // prenet keep bits of step t+1 (8 per row)
   float* s_bias_p = reinterpret_cast<float*>(sp); sp += 8 * 4;                // bias of this CTA's 8 projection columns
+  long long* s_prof = reinterpret_cast<long long*>(sp); sp += 24 * 8;         // phase profile, accumulated on chip
   float* s_pad0 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // previous weights (padded)
   float* s_pad1 = reinterpret_cast<float*>(sp); sp += ((TP + 3) & ~3) * 4;   // cumulative weights (padded)
-  float* s_e = reinterpret_cast<float*>(sp); sp += ntiles * 128 * 4;          // [ntiles * 128] attention weights
-  float* s_ep = reinterpret_cast<float*>(sp);                                 // [4][ntiles * 128] energy partial sums: one writer
-                                                                              // per (column group, position), summed in a fixed
+  // one region, two tenants that are never live together: the hi/lo accumulator exchange of the event epilogues
+  // (s_xch) and the attention's weights / energy partial sums (s_e, s_ep)
+  float* s_xch = reinterpret_cast<float*>(sp);                                // [64][33] lo-row halves of the accumulators
+  float* s_e = reinterpret_cast<float*>(sp);                                  // [ntiles * 128] attention weights
+  float* s_ep = s_e + ntiles * 128;                                           // [4][ntiles * 128] energy partial sums: one writer
+                                                                              // per (group, position), summed in a fixed
                                                                               // order -> bit-reproducible (no shared-memory atomics)
+  (void)s_red;
 
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.cs = p.cluster; rg.rank = p.cluster > 1 ? ptx::cluster_ctarank() : 0;
   rg.pre = 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
+    for (int s = 0; s < p.nstages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], rg.cs); }
     ptx::mbar_init(rg.acc, 1);
     ptx::fence_barrier_init();
   }
@@ -550,11 +595,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
   // phase profile (cycles, accumulated over steps) on three sample CTAs; see t2_decoder_profile()
   const int prof_slot = cta == 0 ? 0 : (cta == 60 ? 1 : (cta == 100 ? 2 : -1));
   long long prof_last = clock64();
+  if (tid < 24) s_prof[tid] = 0;
 #define T2_PROF(ph)                                                        \
   do {                                                                     \
     if (prof_slot >= 0 && tid == 0) {                                      \
       const long long now_ = clock64();                                    \
-      ctrl->prof[prof_slot][ph] += now_ - prof_last;                       \
+      s_prof[ph] += now_ - prof_last;   /* shared memory: a global read-modify-write here stalls the producer thread */ \
       prof_last = now_;                                                    \
     }                                                                      \
   } while (0)
@@ -572,6 +618,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) g[i_] += s_xch[row * kXchStride + cg * 8 + i_]; \
     }                                                                                    \
   } while (0)
+
+  // epilogue of E4 on the prenet-2 CTAs: x2 = relu(W_2 x1) * mask * 2 -> x2 image            model.py:97-100
+  auto x2_epilogue = [&]() {
+    float g[8];
+    if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
+    if (cg == 0 && is_lo) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (cg == 0 && erow) {
+      const int col0 = (cta - kX2Cta0) * 8;
+      float r[8];
+      const uint32_t bits = s_mask[row];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        r[j] = ((bits >> j) & 1u) ? fmaxf(g[j] + s_xch[row * kXchStride + j], 0.f) * 2.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) store_split2(p.x2_img, row, col0 + j, r[j], r[j + 1]);
+    }
+  };
 
   int t = 0;
   for (; t < p.cap; ++t) {
@@ -662,49 +730,51 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     const bool att_cta = (cta & 63) < p.B;
     const int att_b = cta & 63, ahalf = cta >> 6;
     uint8_t* aimg = rg.stage0;
-    const int smem_rows = min(T, (kStages * kStageBytes) / (kEnc / 2 * 4));   // memory rows staged in the ring
-    auto att_im2col_mma = [&](int t0, int nt) {
-      const int j_end = min(T, (t0 + nt) * 128);
-      // (1) im2col image of the [previous | cumulative] weights, A[j][ch*31+k] = pad_ch[j+k], as split-fp16
-      //     SWIZZLE_128B tiles of 128 rows in the (idle) operand ring; rows >= T stay stale: their
-      //     accumulator rows are never read                                        model.py:23
-      for (int item = t0 * 128 * 8 + tid; item < j_end * 8; item += kThreads) {
-        const int j = item >> 3, g8 = item & 7;
-        const int tile = (j >> 7) - t0, r = j & 127;
+    // the idle operand ring during the attention phase: [im2col image: hi plane | lo plane][encoder-memory rows of this CTA]
+    const int att_rounds = (T + 255) >> 8;
+    const int img_plane = att_rounds > 1 ? 32768 : max(4096, ((T + 15) & ~15) * 128);
+    const int img_bytes = 2 * img_plane;
+    const int smem_rows = min(T, (p.nstages * kStageBytes - img_bytes) / (kEnc / 2 * 4));   // memory rows staged in the ring
+    // pa^T = Weff . A^T on the tensor cores (fused model.py:23-25), i.e. the fused filter bank is the M = 128 operand (TMEM lane =
+    // attention dim d) and the positions are the N dimension (accumulator column = position, N = T_enc rounded up
+    // to 16, <= 256 per round).  Every warp then owns a slice of POSITIONS of all 128 dims, so the 19,200 tanh of a
+    // row spread evenly over the four SM sub-partitions for any T_enc (position-major tiles put the partial last
+    // tile on one sub-partition: 64 vs 32 tanh per thread at T_enc = 150), the processed-memory reads are
+    // coalesced (lanes = consecutive dims) and can be issued before the q barrier.
+    auto att_im2col_mma_tr = [&](int r0) {
+      const int jbase = r0 * 256, cnt = min(T - jbase, 256), npad = (cnt + 15) & ~15;
+      for (int item = tid; item < npad * 8; item += kThreads) {
+        const int jj = item >> 3, g8 = item & 7, j = jbase + jj;
         __align__(16) __half hh[8];
         __align__(16) __half ll[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int kk = g8 * 8 + e;
           float v = 0.f;
-          if (kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
+          if (jj < cnt && kk < 2 * kLocK) v = kk < kLocK ? s_pad0[j + kk] : s_pad1[j + kk - kLocK];
           split_fp16(v, hh[e], ll[e]);
         }
-        uint8_t* dst = aimg + tile * 32768 + (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) * 16);
+        uint8_t* dst = aimg + (jj >> 3) * 1024 + (jj & 7) * 128 + ((g8 ^ (jj & 7)) * 16);
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(ll);
+        *reinterpret_cast<uint4*>(dst + img_plane) = *reinterpret_cast<const uint4*>(ll);
       }
       ptx::fence_proxy_async();
       __syncthreads();
-      // (2) processed attention weights pa = A . Weff^T on the tensor cores (fused model.py:23-25):
-      //     M = 128 positions per tile, N = 128 attention dims, K = 64 (62 taps), split-fp16 3-pass
       if (warp == 1) {
         if (lane == 0) {
           ptx::tc_fence_after();
-          const uint32_t as = ptx::smem_u32(aimg), bs = ptx::smem_u32(s_weff);
-          const uint32_t idesc = ptx::make_idesc_f16(128, 128);
-          for (int tile = 0; tile < nt; ++tile) {
-            const uint32_t d = tmem_base + kColAtt + tile * 128;
+          const uint32_t ws = ptx::smem_u32(s_weff), ps = ptx::smem_u32(aimg);
+          const uint32_t idesc = ptx::make_idesc_f16(128, (uint32_t)npad);
+          const uint32_t d = tmem_base + kColAtt;
 #pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
-              const uint64_t a_hi = ptx::make_sw128_desc(as + tile * 32768 + kk * 32);
-              const uint64_t a_lo = ptx::make_sw128_desc(as + tile * 32768 + 16384 + kk * 32);
-              const uint64_t b_hi = ptx::make_sw128_desc(bs + kk * 32);
-              const uint64_t b_lo = ptx::make_sw128_desc(bs + 16384 + kk * 32);
-              ptx::umma_f16(d, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
-              ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
-              ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
-            }
+          for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            const uint64_t w_hi = ptx::make_sw128_desc(ws + kk * 32);
+            const uint64_t w_lo = ptx::make_sw128_desc(ws + 16384 + kk * 32);
+            const uint64_t p_hi = ptx::make_sw128_desc(ps + kk * 32);
+            const uint64_t p_lo = ptx::make_sw128_desc(ps + (uint32_t)img_plane + kk * 32);
+            ptx::umma_f16(d, w_hi, p_hi, idesc, kk > 0 ? 1u : 0u);
+            ptx::umma_f16(d, w_lo, p_hi, idesc, 1u);
+            ptx::umma_f16(d, w_hi, p_lo, idesc, 1u);
           }
           ptx::umma_commit(rg.acc);
         }
@@ -712,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       }
     };
     auto stage_memory_rows = [&](int j0, int j1) {     // cp.async this CTA's half of memory rows [j0, j1) into the ring
-      const uint32_t sbase = ptx::smem_u32(rg.stage0);
+      const uint32_t sbase = ptx::smem_u32(rg.stage0) + (uint32_t)img_bytes;
       const float* msrc = p.memory + (long)att_b * T * kEnc + ahalf * (kEnc / 2);
       for (int i = j0 * 64 + tid; i < j1 * 64; i += kThreads) {
         const int j = i >> 6, c4 = i & 63;
@@ -723,9 +793,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     grid_arrive(ctrl, bar_target);                                             // B2 (arrive): q written
+    const int adim = quad * 32 + lane;     // this thread's attention dim = its TMEM lane
+    float pm_next[8];                      // processed-memory values of the thread's next chunk of 8 positions (software pipeline)
+    auto load_pm = [&](const float* pmr, int j0, int cnt) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pm_next[e] = (j0 + e < cnt) ? __ldg(pmr + (long)(j0 + e) * kAtt) : 0.f;
+    };
     if (att_cta) {
-      att_im2col_mma(0, min(2, ntiles));
-      if (smem_rows > 64) stage_memory_rows(64, smem_rows);   // ring space beyond the 2-tile A image
+      att_im2col_mma_tr(0);
+      stage_memory_rows(0, smem_rows);     // everything the context needs is in flight before the q barrier
+      load_pm(p.pm + (long)att_b * T * kAtt + adim, cg * 8, min(T, 256));
     }
     T2_PROF(15);
     grid_wait(ctrl, bar_target);                                               // B2 (wait): q complete
@@ -734,60 +811,64 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       const int b = att_b;
       for (int i = tid; i < kAtt; i += kThreads) s_q[i] = __ldcg(&p.q[b * kAtt + i]);
       __syncthreads();
-      for (int t0 = 0; t0 < ntiles; t0 += 2) {            // rounds of up to 2 tiles of 128 positions
-        const int nt = min(2, ntiles - t0);
-        int nact = 0;
-        for (int tl = 0; tl < nt; ++tl)
-          if ((t0 + tl) * 128 + quad * 32 < T) nact = tl + 1;
-        if (t0 > 0) att_im2col_mma(t0, nt);
-        mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
-        rg.acc_phase ^= 1;
-        ptx::tc_fence_after();
-        T2_PROF(16);
-        if (t0 + 2 >= ntiles) stage_memory_rows(0, min(64, smem_rows));   // the A image region is free now
-        // (3) energies e_j = v . tanh(q + pa_j + pm_j): accumulator row j = TMEM lane; the 4 warps of a
-        //     lane quadrant split the 128 columns (x active tiles) in chunks of 8     model.py:58-60
-        {
-          float part = 0.f;
-          int cur_tile = -1;
-          for (int c0 = cg; c0 < nact * 16; c0 += 4 * (kWarps / 4)) {
-            float4 pf[4][2];      // processed-memory rows, fetched 4 chunks at a time
+      {
+        const int eN = ntiles * 128;
+        const float qd = s_q[adim], vd = s_v[adim];
+        const int nrounds = att_rounds;
+        for (int r0 = 0; r0 < nrounds; ++r0) {
+          const int jbase = r0 * 256, cnt = min(T - jbase, 256), nch = (((cnt + 15) & ~15) >> 3);
+          if (r0 > 0) att_im2col_mma_tr(r0);
+          mbar_wait(rg.acc, rg.acc_phase, ctrl, 203);
+          rg.acc_phase ^= 1;
+          ptx::tc_fence_after();
+          T2_PROF(16);
+          // energies e_j = sum_d v_d tanh(q_d + pa_dj + pm_jd): this thread adds dim d = adim for the 8 positions of
+          // each of its chunks, then the 32 dims of the warp are summed with a transpose-reduce (9 shuffles per 8
+          // positions, fixed order); the four 32-dim groups of a position are added in a fixed order at the softmax
+          const float* pmr = p.pm + ((long)b * T + jbase) * kAtt + adim;
+          if (r0 > 0) load_pm(pmr, cg * 8, cnt);
+#pragma unroll 1
+          for (int c = cg; c < nch; c += 4) {
+            const int j0 = c * 8;
+            float pm8[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int c = c0 + u * (kWarps / 4);
-              const int j = (t0 + (c >> 4)) * 128 + quad * 32 + lane;
-              if (c < nact * 16 && j < T) {
-                const float* pmr = p.pm + ((long)b * T + j) * kAtt + (c & 15) * 8;
-                pf[u][0] = __ldg(reinterpret_cast<const float4*>(pmr));
-                pf[u][1] = __ldg(reinterpret_cast<const float4*>(pmr + 4));
-              } else {
-                pf[u][0] = pf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = 0; e < 8; ++e) pm8[e] = pm_next[e];
+            if (c + 4 < nch) load_pm(pmr, j0 + 32, cnt);           // next chunk's loads fly during this chunk's tanh
+            float g[8], sv[8];
+            ptx::tmem_ld8(t_lane + kColAtt + j0, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv[e] = vd * tanh_fast(qd + g[e] + pm8[e]);
+            float r4[4], r2[2], r1;
+            {
+              const bool up = (lane & 16) != 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float send = up ? sv[e] : sv[e + 4], keep = up ? sv[e + 4] : sv[e];
+                r4[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
               }
             }
+            {
+              const bool up = (lane & 8) != 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int c = c0 + u * (kWarps / 4);
-              if (c >= nact * 16) break;
-              const int tile = c >> 4, col0 = (c & 15) * 8;
-              if (tile != cur_tile) {
-                if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) s_ep[cg * ntiles * 128 + jp] = part; }
-                part = 0.f; cur_tile = tile;
-              }
-              const int j = (t0 + tile) * 128 + quad * 32 + lane;
-              float g[8];
-              ptx::tmem_ld8(t_lane + kColAtt + tile * 128 + col0, g);
-              if (j < T) {
-                const float pmv[8] = {pf[u][0].x, pf[u][0].y, pf[u][0].z, pf[u][0].w, pf[u][1].x, pf[u][1].y, pf[u][1].z, pf[u][1].w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) part = fmaf(s_v[col0 + i], tanh_fast(s_q[col0 + i] + g[i] + pmv[i]), part);
+              for (int e = 0; e < 2; ++e) {
+                const float send = up ? r4[e] : r4[e + 2], keep = up ? r4[e + 2] : r4[e];
+                r2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
               }
             }
+            {
+              const bool up = (lane & 4) != 0;
+              const float send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
+              r1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+            const int jj = j0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && jj < cnt) s_ep[quad * eN + jbase + jj] = r1;
           }
-          if (cur_tile >= 0) { const int jp = (t0 + cur_tile) * 128 + quad * 32 + lane; if (jp < T) s_ep[cg * ntiles * 128 + jp] = part; }
+          ptx::tc_fence_before();
+          __syncthreads();
+          T2_PROF(17);
         }
-        ptx::tc_fence_before();
-        __syncthreads();
-        T2_PROF(17);
       }
       // mask + softmax (model.py:79-82): every warp reduces all T energies itself (shuffles only, no
       // cross-warp exchange), then the threads split the normalised write-out
@@ -813,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       T2_PROF(18);
       {                                                           // context = aw . memory  model.py:83-84
         const int c4 = tid & 63, jg = tid >> 6;                   // 64 float4 = this CTA's 256 columns; 8 j-groups
-        const float4* ms = reinterpret_cast<const float4*>(rg.stage0);
+        const float4* ms = reinterpret_cast<const float4*>(rg.stage0 + img_bytes);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int j = jg; j < smem_rows; j += 8) {
@@ -928,47 +1009,32 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
       }
       __syncthreads();
-      if (has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel && tid == 0) {   // the gate CTA
-        atomicMax(p.n_steps, t + 1);
-        if (p.infer && *s_live == 0) ctrl->all_done = 1;
-        __threadfence();
-      }
+      const bool gate_cta = has_p && (cta - kPCta0) * 8 <= kMel && (cta - kPCta0) * 8 + 8 > kMel;
+      if (gate_cta && tid == 0) atomicMax(p.n_steps, t + 1);
       T2_PROF(11);
       if (!p.infer) continue;                                                  // teacher forcing: x2 is precomputed
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B5: x1 / stop flag complete
-      T2_PROF(12);
-      int all_done;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(all_done) : "l"(&ctrl->all_done) : "memory");
-      if (all_done || t + 1 == p.cap) { ++t; break; }
-    }
-    // ======== E4: x1 -> x2_(t+1) (second prenet layer) ================================ model.py:97-100
-    {
-      run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, &plan.ev[0]);   // step t+1 is certain here
+      // x1 has 43 producers (the projection CTAs) and 32 consumers (the prenet-2 CTAs), x2 has those 32 producers and
+      // everybody as consumer: two producer-scoped arrival counters instead of two 128-way barriers -- nobody but
+      // the 32 prenet-2 CTAs waits for x1.  The stop decision rides on the counters (bits 24+): the gate CTA adds
+      // kStopFlag to its x1 arrival when every row has fired, the prenet-2 CTAs pass it on with their x2 arrival.
+      bool stop = t + 1 == p.cap;
+      if (has_p) signal_counter(&ctrl->x1_count, 1u + ((gate_cta && *s_live == 0) ? kStopFlag : 0u));
       if (has_x2) {
-        float g[8];
-        if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
-        if (cg == 0 && is_lo) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s_xch[row * kXchStride + i] = g[i];
+        stop |= wait_counter(&ctrl->x1_count, (unsigned int)(kPCtas * (t + 1)), s_flag, ctrl, 102);
+        if (!stop) {
+          run_event(rg, plan.ev[4], p.x1_img, p.wimg, 4, tmem_base, ctrl, nullptr);    // E4: x1 -> x2_(t+1)  model.py:97-100
+          x2_epilogue();
         }
-        ptx::tc_fence_before();
-        __syncthreads();
-        if (cg == 0 && erow) {
-          const int col0 = (cta - kX2Cta0) * 8;
-          float r[8];
-          const uint32_t bits = s_mask[row];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            r[j] = ((bits >> j) & 1u) ? fmaxf(g[j] + s_xch[row * kXchStride + j], 0.f) * 2.f : 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) store_split2(p.x2_img, row, col0 + j, r[j], r[j + 1]);
-        }
+        signal_counter(&ctrl->x2_count, 1u + (stop ? kStopFlag : 0u));
       }
-      T2_PROF(13);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B6: x2_(t+1) complete
+      T2_PROF(12);
+      stop |= wait_counter(&ctrl->x2_count, (unsigned int)(kX2Ctas * (t + 1)), s_flag, ctrl, 103);
       T2_PROF(14);
+      if (stop) { ++t; break; }
     }
   }
+  if (prof_slot >= 0 && tid == 0)
+    for (int i = 0; i < 24; ++i) ctrl->prof[prof_slot][i] = s_prof[i];
   // rows that never fired: length = number of steps run (model.py:445-447)
   if (cta == 0) {
     __syncthreads();
@@ -981,9 +1047,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
     // every stage this CTA filled has been released by all peers (their commits arrive on OUR
     // barriers) before anyone leaves, then leave together
     if (tid == 0)
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < p.nstages; ++s) {
         mbar_wait(&rg.empty[rg.p_stage], rg.p_phase ^ 1, ctrl, 204);
-        if (++rg.p_stage == kStages) { rg.p_stage = 0; rg.p_phase ^= 1; }
+        if (++rg.p_stage == rg.ns) { rg.p_stage = 0; rg.p_phase ^= 1; }
       }
     __syncthreads();
     ptx::cluster_sync_all();
@@ -998,11 +1064,21 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static size_t persistent_smem_bytes(int T) {
+static size_t persistent_smem_bytes(int T, int nstages) {
   const int TP = T + kLocK - 1;
   const int ntiles = (T + 127) / 128;
-  return (size_t)kStages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
-         (size_t)kRows * kXchStride * 4 + kRows * 4 + 32 + 2 * (size_t)((TP + 3) & ~3) * 4 + (size_t)5 * ntiles * 128 * 4 + 1024;
+  const size_t xch = (size_t)kRows * kXchStride * 4, att = (size_t)5 * ntiles * 128 * 4;   // one shared region
+  return (size_t)nstages * kStageBytes + kWeffBytes + 16 * 8 + 16 + 16 + 2 * 32 * 4 + kAtt * 4 + kAtt * 4 + 32 * 4 +
+         kRows * 4 + 32 + 24 * 8 + 2 * (size_t)((TP + 3) & ~3) * 4 + (xch > att ? xch : att) + 1024;
+}
+constexpr size_t kSmemLimit = 227 * 1024;
+// 5 ring stages when they fit beside the T_enc-dependent attention state (T_enc <~ 330), else 4
+static int persistent_stages(int T) {
+  int want = 4;                 // 5 stages measured no faster than 4 on B200 (profiles/r02_decoder_ab.md): default 4
+  const char* e = getenv("T2_STAGES");
+  if (e && atoi(e) >= 3 && atoi(e) <= kMaxStages) want = atoi(e);
+  while (want > 4 && persistent_smem_bytes(T, want) > kSmemLimit) --want;
+  return want;
 }
 
 size_t persistent_ws_bytes(int B, int T, int cap) {
@@ -1016,7 +1092,7 @@ size_t persistent_ws_bytes(int B, int T, int cap) {
 bool persistent_supported(const T2Model* m, const T2DecoderArgs* a) {
   if (!m->pk) return false;
   if (m->sm_count < kG) return false;
-  if (persistent_smem_bytes(a->T_enc) > 227 * 1024) return false;
+  if (persistent_smem_bytes(a->T_enc, 4) > kSmemLimit) return false;
   return true;
 }
 
@@ -1038,6 +1114,7 @@ int persistent_pack_create(T2Model* m, cudaStream_t s) {
       for (int n : ns) { e.n[e.ncons++] = n; e.nrows += n; }
       e.w_bytes = (uint32_t)e.nrows * 256;
       e.w_off = (uint32_t)off;
+      e.chunks = chunks;
       off += (size_t)chunks * e.w_bytes;
     };
     set(0, 4, kColA, {32});
@@ -1187,7 +1264,10 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
     T2_LAUNCH_CHECK();
     p.teacher_x2_img = timg;
   }
-  const size_t smem = persistent_smem_bytes(T);
+  p.nstages = persistent_stages(T);
+  {
+  }
+  const size_t smem = persistent_smem_bytes(T, p.nstages);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   // TMA multicast of the activation chunks over clusters (T2_CLUSTER = 2 / 4 / 8) is implemented and
@@ -1236,12 +1316,13 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
     le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
   }
   if (le != cudaSuccess) return fail(T2_ERR_CUDA, "persistent decoder launch failed: %s", cudaGetErrorString(le));
-  if (getenv("T2_VERBOSE")) fprintf(stderr, "[t2b200] persistent decoder: B=%d T_enc=%d cap=%d cluster=%d hier_barrier=%d smem=%zu\n",
-                                    B, T, cap, p.cluster, p.hier_barrier, smem);
+  if (getenv("T2_VERBOSE")) fprintf(stderr, "[t2b200] persistent decoder: B=%d T_enc=%d cap=%d cluster=%d stages=%d smem=%zu\n",
+                                    B, T, cap, p.cluster, p.nstages, smem);
   g_launch_count++;
   return T2_OK;
 }
 
+#ifdef T2_SELFTEST
 // ---------------------------------------------------------------------------------------------
 // self test of the tcgen05 engine: C (64 x N) = 2 * A (64 x K) . W (N x K)^T with the same run_event()
 // (two accumulating passes over the ring) and the same hi/lo accumulator read-out as the decoder.
@@ -1261,7 +1342,7 @@ selftest_kernel(const uint8_t* x_img, const uint8_t* w_img, EventPlan ep, int ch
   float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = rg.pol_w = ptx::policy_evict_last();
-  rg.cs = 1; rg.rank = 0; rg.pre = 0;
+  rg.cs = 1; rg.rank = 0; rg.pre = 0; rg.ns = kStages;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);
@@ -1311,7 +1392,7 @@ int selftest_umma(const float* A, const float* W, int N, int K, int passes, floa
   T2_CUDA(cudaMalloc((void**)&ctrl, sizeof(DecoderCtrl)));
   T2_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(DecoderCtrl), s));
   EventPlan ep; memset(&ep, 0, sizeof(ep));
-  ep.ncons = 1; ep.n[0] = N; ep.nrows = N; ep.col0 = 0; ep.w_bytes = N * 256; ep.w_off = 0;
+  ep.ncons = 1; ep.n[0] = N; ep.nrows = N; ep.col0 = 0; ep.w_bytes = N * 256; ep.w_off = 0; ep.chunks = chunks;
   rows_to_image_kernel<<<dim3(chunks, 1), 256, 0, s>>>(A, K, kRows, K, 0, ximg, 0);
   T2_LAUNCH_CHECK();
   pack_rows_image_kernel<<<chunks, 256, 0, s>>>(W, N, K, wimg);
@@ -1325,6 +1406,8 @@ int selftest_umma(const float* A, const float* W, int N, int K, int passes, floa
   return T2_OK;
 }
 
+
+#endif  // T2_SELFTEST
 
 // ---------------------------------------------------------------------------------------------
 // Backward skinny GEMMs of the training path on the tensor cores (decoder_backward.cu, KB / KE):
@@ -1373,7 +1456,7 @@ bwd_gemm_kernel(const uint8_t* __restrict__ x_img, const uint8_t* __restrict__ w
   float* s_xch = reinterpret_cast<float*>(sp);                 // [64][80]
   rg.p_stage = rg.p_phase = rg.c_stage = rg.c_phase = rg.acc_phase = 0;
   rg.pol_x = ptx::policy_evict_last(); rg.pol_w = ptx::policy_evict_first();
-  rg.cs = 1; rg.rank = 0; rg.pre = 0;
+  rg.cs = 1; rg.rank = 0; rg.pre = 0; rg.ns = kStages;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&rg.full[s], 1); ptx::mbar_init(&rg.empty[s], 1); }
     ptx::mbar_init(rg.acc, 1);
@@ -1442,7 +1525,7 @@ int bwd_gemm_prepare(T2Model* m, cudaStream_t s) {
           memset(&c, 0, sizeof(c));
           c.chunk0 = sp * chunks / kBwdGemmSplit; c.nchunks = (sp + 1) * chunks / kBwdGemmSplit - c.chunk0;
           c.col0 = t * tile; c.split = sp;
-          c.ep.nrows = tile; c.ep.col0 = 0; c.ep.ncons = 1; c.ep.n[0] = tile; c.ep.w_bytes = w_bytes;
+          c.ep.nrows = tile; c.ep.col0 = 0; c.ep.ncons = 1; c.ep.n[0] = tile; c.ep.w_bytes = w_bytes; c.ep.chunks = c.nchunks;
           c.ep.w_off = (uint32_t)(((size_t)t * chunks + c.chunk0) * w_bytes);
         }
       T2_CUDA(cudaMalloc((void**)&pk->bwd_plans[which], sizeof(BwdCta) * ncta));

@@ -30,7 +30,8 @@ struct T2Model {
 
   // ---- packed operands of the persistent decoder kernel (owned; see decoder_persistent.cu) ----
   void* pk = nullptr;            // opaque PersistentPack*
-  void* blas = nullptr;          // cublasHandle_t of the backward pass (time-batched plain GEMMs), created lazily
+  void* blas = nullptr;          // cublasHandle_t: only for the T2_GEMM=cublas cross-check of the training path, created lazily
+  void* gemm_ws = nullptr; size_t gemm_ws_bytes = 0;   // scratch of gemm_tc.cu (operand scales, split-K partial tiles)
 };
 
 namespace t2 {

@@ -7,7 +7,6 @@
 // gradient g_x = sum_k G_z[r+2-k] W_k, weight gradient dW_k = G_z^T X[r+k-2].  These are plain library GEMMs
 // (cuBLAS); BatchNorm statistics / normalisation / activation / dropout and their backward are our kernels.
 // BiLSTM backward: reverse recurrence with one skinny GEMM + one elementwise kernel per step and direction.
-#include <cublas_v2.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -19,10 +18,10 @@
 
 namespace t2 {
 
-int blas_handle(T2Model* m, cudaStream_t s, cublasHandle_t* out);
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+int colsum_rm(T2Model* m, cudaStream_t s, const float* X, long ld, long rows, int cols, float* out);
+int gemm_rm(T2Model* m, cudaStream_t s, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
             float* C, long ldc, float beta);
-int gemm_rm_wgrad(cublasHandle_t h, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
+int gemm_rm_wgrad(T2Model* m, cudaStream_t s, bool ta, bool tb, int M, int N, int K, const float* A, long lda, const float* B, long ldb,
                   float* C, long ldc, float beta);
 
 namespace {
@@ -400,7 +399,7 @@ int conv_wgrad_tc(const ConvLayer& L, int B, int T, const float* gz_p, const flo
   return T2_OK;
 }
 
-int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* xp, float* zp,
+int conv_fwd(T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* xp, float* zp,
              float* stats, float* yp, float* y_plain, bool update_running, float* partial, const TcTrain* tc, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
   const int Me = (int)(Mp - 2 * kPadRows);
@@ -408,7 +407,7 @@ int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
     T2_TRY(tc_train_conv(m, xp, L.cin, L.wimg_fwd, L.cout, B, T, zp, tc->planes, nullptr, nullptr, s));
   } else {
     for (int k = 0; k < kConvK; ++k)
-      T2_TRY(gemm_rm(bl, false, true, Me, L.cout, L.cin, xp + (long)k * L.cin, L.cin, L.wpk + (long)k * L.cin, (long)kConvK * L.cin,
+      T2_TRY(gemm_rm(m, s, false, true, Me, L.cout, L.cin, xp + (long)k * L.cin, L.cin, L.wpk + (long)k * L.cin, (long)kConvK * L.cin,
                      zp + (long)kPadRows * L.cout, L.cout, k ? 1.f : 0.f));
   }
   {
@@ -436,7 +435,7 @@ int conv_fwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
 
 // g: gradient wrt the layer output (padded or plain rows).  Writes gx_p (padded rows, garbage in the pad rows) when
 // non-null, and the gradients of conv.weight / conv.bias / bn.weight / bn.bias.
-int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* g, int g_padded,
+int conv_bwd(T2Model* m, const ConvLayer& L, int B, int T, int training, uint64_t seed, const float* g, int g_padded,
              const float* xp, const float* zp, const float* stats, const float* yp, float* gz_p, float* gx_p, float* sums, float* dwpk,
              const float* ones, float* const* G, const WgConvWs* wg, const TcTrain* tc, cudaStream_t s) {
   const long Mp = (long)B * (T + 2 * kPadRows);
@@ -457,10 +456,10 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
   if (wg) {   // weight + bias gradient on our tcgen05 engine
     T2_TRY(conv_wgrad_tc(L, B, T, gz_p, xp, G[L.wbase], G[L.wbase + 1], *wg, s));
   } else {
-    if (G[L.wbase + 1]) T2_TRY(gemm_rm(bl, false, false, 1, L.cout, (int)Mp, ones, Mp, gz_p, L.cout, G[L.wbase + 1], L.cout, 0.f));      // d conv bias
+    if (G[L.wbase + 1]) T2_TRY(colsum_rm(m, s, gz_p, L.cout, Mp, L.cout, G[L.wbase + 1]));      // d conv bias
     if (G[L.wbase]) {
       for (int k = 0; k < kConvK; ++k)
-        T2_TRY(gemm_rm_wgrad(bl, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
+        T2_TRY(gemm_rm_wgrad(m, s, true, false, L.cout, L.cin, Me, gz_p + (long)kPadRows * L.cout, L.cout, xp + (long)k * L.cin, L.cin,
                        dwpk + (long)k * L.cin, (long)kConvK * L.cin, 0.f));
       const long nw = (long)L.cout * L.cin * kConvK;
       unpack_conv_grad_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(dwpk, G[L.wbase], L.cout, L.cin, kConvK);
@@ -479,7 +478,7 @@ int conv_bwd(cublasHandle_t bl, T2Model* m, const ConvLayer& L, int B, int T, in
     T2_TRY(tc_train_conv(m, gz_p, L.cout, *L.wimg_dgrad, L.cin, B, T, gx_p, tc->planes, wg->colsum, wg->stat, s));
   } else if (gx_p) {
     for (int k = 0; k < kConvK; ++k)
-      T2_TRY(gemm_rm(bl, false, false, Me, L.cin, L.cout, gz_p + (long)(2 * kPadRows - k) * L.cout, L.cout, L.wpk + (long)k * L.cin,
+      T2_TRY(gemm_rm(m, s, false, false, Me, L.cin, L.cout, gz_p + (long)(2 * kPadRows - k) * L.cout, L.cout, L.wpk + (long)k * L.cin,
                      (long)kConvK * L.cin, gx_p + (long)kPadRows * L.cin, L.cin, k ? 1.f : 0.f));
   }
   return T2_OK;
@@ -637,8 +636,6 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
   if (a->stash_bytes < postnet_stash_bytes(B, T)) return fail(T2_ERR_WORKSPACE, "postnet stash too small");
   StackStash st;
   const size_t used = stack_carve((char*)a256((size_t)a->stash), B, T, 5, kPostCh, &st);
-  cublasHandle_t bl;
-  T2_TRY(blas_handle(m, s, &bl));
   T2_CUDA(cudaMemsetAsync(st.x[0], 0, used, s));      // zero pad rows everywhere
   const long n = (long)B * T * kMel;
   rows_to_padded_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a->mel, a->mel_batch_stride ? a->mel_batch_stride : (long)T * kMel,
@@ -652,7 +649,7 @@ int postnet_forward_train(T2Model* m, const T2PostnetArgs* a, cudaStream_t s) {
     tcw.planes = (__half*)a256((size_t)a->ws); tc = &tcw;
   }
   for (int i = 0; i < 5; ++i)
-    T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.x[i], st.z[i], st.stats[i], st.x[i + 1], nullptr, a->training != 0,
+    T2_TRY(conv_fwd(m, L[i], B, T, a->training, a->seed, st.x[i], st.z[i], st.stats[i], st.x[i + 1], nullptr, a->training != 0,
                     st.stats[i] + 2 * L[i].cout, tc, s));
   rows_to_bct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.x[5], a->add_residual ? st.x[0] : nullptr, a->mel_post, B, T, kMel);
   T2_LAUNCH_CHECK();
@@ -689,8 +686,6 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
   p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023) + wgconv_bytes(B, T, nullptr, nullptr);
   TcTrain tcw; const TcTrain* tc = nullptr;
   if (use_tc_train()) { tcw.planes = (__half*)a256((size_t)p); tc = &tcw; }
-  cublasHandle_t bl;
-  T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)Mp);
   T2_LAUNCH_CHECK();
   const long n = (long)B * T * kMel;
@@ -705,7 +700,7 @@ int postnet_backward(T2Model* m, const T2PostnetBwdArgs* a, cudaStream_t s) {
       mask_padded_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.x[0], a->wgrad_lengths, B, T, kMel);
       T2_LAUNCH_CHECK();
     }
-    T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.x[i], st.z[i], st.stats[i], st.x[i + 1], gz, gx, sums, dwpk,
+    T2_TRY(conv_bwd(m, L[i], B, T, a->training, a->seed, g, g_padded, st.x[i], st.z[i], st.stats[i], st.x[i + 1], gz, gx, sums, dwpk,
                     ones, a->grads, wg, tc, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;
@@ -737,8 +732,6 @@ int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, cons
   if (a->stash_bytes < encoder_stash_bytes(B, T)) return fail(T2_ERR_WORKSPACE, "encoder stash too small");
   EncStash st;
   enc_carve((char*)a256((size_t)a->stash), B, T, &st);
-  cublasHandle_t bl;
-  T2_TRY(blas_handle(m, s, &bl));
   const size_t cs_bytes = stack_carve(nullptr, B, T, 3, kEncCh, nullptr);
   T2_CUDA(cudaMemsetAsync(st.cs.x[0], 0, cs_bytes, s));
   const long n = (long)B * T * kEnc;
@@ -750,7 +743,7 @@ int encoder_convs_train(T2Model* m, const T2EncoderArgs* a, cudaStream_t s, cons
   TcTrain tcw; const TcTrain* tc = nullptr;
   if (use_tc_train() && planes) { tcw.planes = (__half*)planes; tc = &tcw; }
   for (int i = 0; i < 3; ++i)
-    T2_TRY(conv_fwd(bl, m, L[i], B, T, a->training, a->seed, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], i == 2 ? st.xl : nullptr,
+    T2_TRY(conv_fwd(m, L[i], B, T, a->training, a->seed, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], i == 2 ? st.xl : nullptr,
                     a->training != 0, st.cs.stats[i] + 2 * L[i].cout, tc, s));
   *xl = st.xl; *gates = st.gates; *cst = st.cst;
   return T2_OK;
@@ -804,8 +797,6 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   p = (char*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023) + wgconv_bytes(B, T, nullptr, nullptr);
   TcTrain tcw; const TcTrain* tc = nullptr;
   if (use_tc_train()) { tcw.planes = (__half*)a256((size_t)p); tc = &tcw; }
-  cublasHandle_t bl;
-  T2_TRY(blas_handle(m, s, &bl));
   fill1_kernel<<<(unsigned)((n_ones + 255) / 256), 256, 0, s>>>(ones, 1.f, (long)n_ones);
   T2_LAUNCH_CHECK();
   T2_CUDA(cudaMemsetAsync(g_c, 0, (size_t)2 * 64 * kEncH * 4, s));
@@ -826,15 +817,15 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   for (int dir = 0; dir < 2; ++dir) {
     const int wb = W_ENC_LSTM + 4 * dir;
     const float* dGd = dG + (size_t)dir * 4 * kEncH;          // rows (b, t), row stride 2048
-    if (G[wb]) T2_TRY(gemm_rm(bl, true, false, 4 * kEncH, kEnc, BT, dGd, 8 * kEncH, st.xl, kEnc, G[wb], kEnc, 0.f));
-    if (G[wb + 1]) T2_TRY(gemm_rm(bl, true, false, 4 * kEncH, kEncH, BT, dGd, 8 * kEncH, hp + (size_t)dir * kEncH, kEnc, G[wb + 1], kEncH, 0.f));
+    if (G[wb]) T2_TRY(gemm_rm(m, s, true, false, 4 * kEncH, kEnc, BT, dGd, 8 * kEncH, st.xl, kEnc, G[wb], kEnc, 0.f));
+    if (G[wb + 1]) T2_TRY(gemm_rm(m, s, true, false, 4 * kEncH, kEncH, BT, dGd, 8 * kEncH, hp + (size_t)dir * kEncH, kEnc, G[wb + 1], kEncH, 0.f));
     if (G[wb + 2] || G[wb + 3]) {
-      T2_TRY(gemm_rm(bl, false, false, 1, 4 * kEncH, BT, ones, BT, dGd, 8 * kEncH, tmp, 4 * kEncH, 0.f));
+      T2_TRY(colsum_rm(m, s, dGd, 8 * kEncH, BT, 4 * kEncH, tmp));
       if (G[wb + 2]) T2_CUDA(cudaMemcpyAsync(G[wb + 2], tmp, 4 * kEncH * 4, cudaMemcpyDeviceToDevice, s));
       if (G[wb + 3]) T2_CUDA(cudaMemcpyAsync(G[wb + 3], tmp, 4 * kEncH * 4, cudaMemcpyDeviceToDevice, s));
     }
     // gradient wrt the LSTM input: dG_dir (BT x 1024) . W_ih_dir (1024 x 512)
-    T2_TRY(gemm_rm(bl, false, false, BT, kEnc, 4 * kEncH, dGd, 8 * kEncH, m->w[wb], kEnc, dxl, kEnc, dir ? 1.f : 0.f));
+    T2_TRY(gemm_rm(m, s, false, false, BT, kEnc, 4 * kEncH, dGd, 8 * kEncH, m->w[wb], kEnc, dxl, kEnc, dir ? 1.f : 0.f));
   }
   // ---- conv stack ----
   ConvLayer L[3];
@@ -843,7 +834,7 @@ int encoder_backward(T2Model* m, const T2EncoderBwdArgs* a, cudaStream_t s) {
   float* gx = gxa;
   for (int i = 2; i >= 0; --i) {
     const bool need_gx = i > 0 || a->d_embedded || (a->text && G[W_EMB]);
-    T2_TRY(conv_bwd(bl, m, L[i], B, T, a->training, a->seed, g, g_padded, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], gz,
+    T2_TRY(conv_bwd(m, L[i], B, T, a->training, a->seed, g, g_padded, st.cs.x[i], st.cs.z[i], st.cs.stats[i], st.cs.x[i + 1], gz,
                     need_gx ? gx : nullptr, sums, dwpk, ones, G, wg, tc, s));
     g = gx; g_padded = 1;
     gx = gx == gxa ? gxb : gxa;

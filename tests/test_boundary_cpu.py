@@ -82,10 +82,17 @@ def test_library_exports_every_declared_symbol():
     _ensure_built()
     header = open(os.path.join(ROOT, "include", "t2b200.h")).read()
     declared = set(re.findall(r"\b(t2_[a-z0-9_]+)\s*\(", header))
-    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    selftests = {n for n in declared if n.startswith("t2_selftest_")}      # declared under #ifdef T2_SELFTEST
+    assert selftests == set(_capi.SELFTEST_EXPORTS), selftests ^ set(_capi.SELFTEST_EXPORTS)
+    assert declared - selftests == set(_capi.EXPORTS), (declared - selftests) ^ set(_capi.EXPORTS)
     L = _capi.lib()
-    for name in declared:
+    for name in declared - selftests:
         assert hasattr(L, name), name
+    for name in selftests:                 # the product library carries no self-test / micro-benchmark code ...
+        assert not hasattr(L, name), name
+    S = _capi.selftest_lib()               # ... the self-test build of the same sources does
+    for name in declared:
+        assert hasattr(S, name), name
     assert L.t2_abi_version() == 1
 
 

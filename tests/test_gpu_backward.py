@@ -9,8 +9,8 @@ import torch
 import tacotron2_b200 as t2
 from oracle import tacotron2_oracle as O
 from tests.common import keep_mask, rel_err, synth_state_dict
-from tests.test_oracle_golden import (GRADS, check_grads_vs_fixture, full_grad_inputs, grad_inputs, load,
-                                      oracle_train_step)
+from tests.test_oracle_golden import (GRADS, check_grads_vs_fixture, check_grads_vs_fp64_fixture, full_grad_inputs,
+                                      grad_inputs, load, oracle_train_step)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -118,7 +118,10 @@ def test_full_train_step_matches_reference_gradient_golden(name):
 def test_full_size_train_step_matches_reference_gradient_golden():
     """BASELINE.json configs[2]: the teacher-forced training step at B=64, T_text=150, T_mel=800 against the gradients
     the REFERENCE's own autograd produced at that size (tools/make_golden.py full grad64: per parameter sum / abs-sum /
-    max + 1024 sampled entries, loss, sub-sampled outputs)."""
+    max + 1024 sampled entries, loss, sub-sampled outputs), in fp32 AND in fp64.  The forward outputs and the loss are
+    held to the fp32 reference at 1e-3 / 1e-4; the gradients to the fp64 reference at max(1e-3, 4 x the deviation of the
+    reference's own fp32 autograd from it) -- that deviation is 1e-3 ... 1e-2 for the encoder convolutions, the
+    embedding and the prenet at this size (printed below)."""
     g = load("full_grad_train_b64_t150_m800")
     sd, text, tl, ol, mels, gt, m = full_grad_inputs(g)
     model = t2.Tacotron2(t2.create_hparams())
@@ -140,7 +143,13 @@ def test_full_size_train_step_matches_reference_gradient_golden():
     assert e_mel < TOL and e_post < TOL and e_gate < TOL
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None for v in grads.values())
-    check_grads_vs_fixture(grads, g, TOL)
+    rep = check_grads_vs_fp64_fixture(grads, g, TOL)
+    worst = sorted(rep.items(), key=lambda kv: -kv[1][0])[:10]
+    print("full-size gradients vs the fp64 reference (engine error, fp32 reference's own error):")
+    for k, (e_eng, e_ref) in worst:
+        print("   %-66s %.2e  %.2e" % (k, e_eng, e_ref))
+    n_better = sum(1 for e_eng, e_ref in rep.values() if e_eng <= e_ref)
+    print("   engine closer to fp64 than the fp32 reference for %d of %d parameters" % (n_better, len(rep)))
 
 
 @pytest.mark.parametrize("B,T", [(3, 21), (5, 64)])
@@ -330,7 +339,8 @@ def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
         gt[i, n - 1:] = 1
     m = dict(pk=keep_mask((Tm + 1, 2, B, 256), 0.5, 1), ak=keep_mask((Tm, B, 1024), 0.1, 2), dk=keep_mask((Tm, B, 1024), 0.1, 3),
              ek=keep_mask((3, B, 512, Tt), 0.5, 4), qk4=keep_mask((4, B, 512, Tm), 0.5, 5), qk1=keep_mask((B, 80, Tm), 0.5, 6))
-    ref_loss, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
+    ref_loss, _, ref_g32 = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
+    _, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, True, dtype=torch.float64)
     model = t2.Tacotron2(t2.create_hparams())
     model.load_state_dict(sd)
     model = model.cuda().train()
@@ -342,12 +352,14 @@ def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
     torch.cuda.synchronize()
     assert abs(loss.item() - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
     gmax = max(float(v.abs().max()) for v in ref_g.values())
-    errs = {}
+    errs, yard = {}, {}
     for k, p in model.named_parameters():
-        # tiny batches make BatchNorm statistics (1-6 samples per channel) badly conditioned: compare against the largest
-        # gradient of the model rather than each tensor's own maximum
-        errs[k] = float((p.grad.detach().cpu().double() - ref_g[k].double()).abs().max()) / gmax
-    print("minimal train step B=%d T_text=%d T_mel=%d: loss %.5f, worst gradient error / max gradient %.2e" % (B, Tt, Tm, loss.item(), max(errs.values())))
-    # BatchNorm over 1-6 samples per channel: rstd up to 1/sqrt(eps) = 316 amplifies the 1e-5 kernel-level differences
-    bad = {k: v for k, v in errs.items() if not v < 1e-2}
+        # tiny batches make BatchNorm statistics (1-6 samples per channel) badly conditioned (rstd up to 1/sqrt(eps) = 316 per
+        # layer amplifies rounding differences): the truth is the oracle in DOUBLE precision, errors are relative to the
+        # largest gradient of the model, and the yardstick is how far the fp32 oracle itself lands from the fp64 one
+        errs[k] = float((p.grad.detach().cpu().double() - ref_g[k]).abs().max()) / gmax
+        yard[k] = float((ref_g32[k].double() - ref_g[k]).abs().max()) / gmax
+    print("minimal train step B=%d T_text=%d T_mel=%d: loss %.5f, worst gradient error / max gradient %.2e (fp32 oracle vs fp64 "
+          "oracle: %.2e)" % (B, Tt, Tm, loss.item(), max(errs.values()), max(yard.values())))
+    bad = {k: (v, yard[k]) for k, v in errs.items() if not v < max(1e-3, 8.0 * yard[k])}
     assert not bad, bad

@@ -45,7 +45,7 @@ def test_umma_split_gemm_selftest(N, K, passes, tol):
     A = torch.randn(64, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     Cd = torch.full((64, N), float("nan"), device="cuda")
-    _capi.check(_capi.lib().t2_selftest_umma(A.data_ptr(), W.data_ptr(), N, K, passes, Cd.data_ptr(),
+    _capi.check_selftest(_capi.selftest_lib().t2_selftest_umma(A.data_ptr(), W.data_ptr(), N, K, passes, Cd.data_ptr(),
                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     ref = 2.0 * (A.double() @ W.double().t())
@@ -231,3 +231,60 @@ def test_half_model_inference_like_the_notebook():
         assert all(x.dtype == (torch.float16 if half else torch.float32) for x in o)
     for a, b in zip(outs[0], outs[1]):
         assert a.shape == b.shape and rel_err(b.float(), a) < 2e-2
+
+
+GEMM_CASES = [
+    # ta, tb, M, N, K, lda_pad, ldb_pad, ldc_pad, beta, batch, scaleA, scaleB
+    (0, 1, 300, 128, 512, 0, 0, 0, 0.0, 1, 1.0, 1.0),            # x . W^T (processed memory / queries)
+    (0, 0, 257, 1536, 81, 0, 0, 0, 0.0, 1, 1e-6, 1.0),           # ld = 81: unaligned rows, K not a multiple of 64
+    (1, 0, 80, 1024, 5000, 1, 0, 512, 0.0, 1, 1e-8, 1.0),        # time-batched weight gradient: small tile, split K
+    (1, 0, 1, 512, 3000, 80, 0, 0, 0.0, 1, 1e-5, 1.0),           # single output row (the gate layer)
+    (0, 0, 1, 4096, 2000, 0, 0, 0, 0.0, 1, 1.0, 1e-7),           # ones . X  (column sums through the GEMM)
+    (1, 0, 128, 64, 70000, 0, 0, 0, 1.0, 1, 1e-4, 1.0),          # location filter gradient chunk: huge K, beta = 1
+    (0, 0, 150, 512, 37, 0, 0, 0, 1.0, 3, 1.0, 1e-3),            # strided batch (d_memory += aw^T . g_ctx), beta = 1
+    (0, 1, 130, 70, 64, 3, 5, 7, 0.5, 1, 1.0, 1.0),              # padded leading dimensions, fractional beta
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_training_path_tensor_core_gemm_vs_fp64(case):
+    """gemm_tc.cu (the tcgen05 split-fp16 GEMM that replaced every cuBLAS sgemm of the training path) against torch fp64:
+    fp32-grade accuracy (error <= 2e-5 of the result's maximum; cuBLAS fp32 lands at ~1e-6) for gradient-like operands
+    many orders of magnitude below 1, rows of wildly different magnitude, unaligned / padded leading dimensions."""
+    ta, tb, M, N, K, pa, pb, pc, beta, batch, sa, sb = case
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a_rows, a_cols = (K, M) if ta else (M, K)
+    b_rows, b_cols = (N, K) if tb else (K, N)
+    lda, ldb, ldc = a_cols + pa, b_cols + pb, N + pc
+    A = torch.randn(batch, a_rows, lda, generator=g) * sa
+    B = torch.randn(batch, b_rows, ldb, generator=g) * sb
+    # rows of op(A) spanning 6 orders of magnitude (per-row operand scales must cope)
+    rs = torch.logspace(0, -6, M).view(1, -1, 1) if not ta else torch.logspace(0, -6, M).view(1, 1, -1)
+    A[:, :, :a_cols] *= rs
+    C0 = torch.randn(batch, M, ldc, generator=g) * (sa * sb)
+    Ad, Bd, Cd = A.cuda(), B.cuda(), C0.clone().cuda()
+    L = _capi.selftest_lib()
+    _capi.check_selftest(L.t2_selftest_gemm_tc(ta, tb, M, N, K, Ad.data_ptr(), lda, Bd.data_ptr(), ldb, Cd.data_ptr(), ldc, beta,
+                                               batch, a_rows * lda, b_rows * ldb, M * ldc,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    opA = A[:, :, :a_cols].double().transpose(1, 2) if ta else A[:, :, :a_cols].double()
+    opB = B[:, :, :b_cols].double().transpose(1, 2) if tb else B[:, :, :b_cols].double()
+    ref = opA @ opB + beta * C0[:, :, :N].double()
+    got = Cd.cpu()[:, :, :N].double()
+    # per output row (rows differ by orders of magnitude): error relative to the row's maximum
+    den = ref.abs().amax(dim=2, keepdim=True).clamp_min(1e-300)
+    err = float(((got - ref).abs() / den).max())
+    assert err < 2e-5, err
+    if pc:   # padding columns of C untouched
+        assert torch.equal(Cd.cpu()[:, :, N:], C0[:, :, N:])
+
+
+def test_column_sums_kernel():
+    g = torch.Generator().manual_seed(0)
+    X = (torch.randn(5000, 90, generator=g) * 1e-4).cuda()
+    out = torch.empty(81, device="cuda")
+    _capi.check_selftest(_capi.selftest_lib().t2_selftest_colsum(X.data_ptr(), 90, 5000, 81, out.data_ptr(),
+                                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    ref = X[:, :81].double().sum(0)
+    assert rel_err(out, ref) < 1e-6

@@ -258,7 +258,8 @@ def gate_targets(ol, T_mel):
     return gt
 
 
-def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0, n_samples=96, keep_outputs=True):
+def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0, n_samples=96, keep_outputs=True,
+              ref64=False):
     """Full training step of the REFERENCE (forward + Tacotron2Loss + backward, autograd) with injected dropout
     masks; the fixture keeps the loss and, per parameter, sum / abs-sum / max of the gradient plus 96 sampled entries."""
     import importlib.util
@@ -305,6 +306,28 @@ def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0, n_sampl
         gr = p_.grad.detach().double().reshape(-1)
         idx = grad_sample_index(k, gr.numel(), n_samples)
         arrays["g/" + k] = torch.cat((torch.stack((gr.sum(), gr.abs().sum(), gr.abs().max())), gr[idx]))
+    if ref64:
+        # The same step through the reference in DOUBLE precision (model.double()): at B=64 / T_mel=800 the reference's
+        # fp32 autograd is itself 1e-3 ... 1e-2 (relative to the gradient's maximum) away from this for the parameters
+        # behind the training-mode BatchNorms, so the fp64 values are what an fp32-grade
+        # implementation is held to, with the fp32 reference's own deviation as the yardstick.
+        model64 = build(sd, training).double()
+        with injected_dropout(ref, MaskInjector(masks)) as inj:
+            out64 = model64((text, tl, mels.double(), int(tl.max()), ol))
+        loss64 = lf.Tacotron2Loss()(out64, (mels.double(), gt.double()))
+        loss64.backward()
+        arrays["loss64"] = loss64.detach()
+        worst = {}
+        for k, p_ in model64.named_parameters():
+            gr = p_.grad.detach().reshape(-1)
+            idx = grad_sample_index(k, gr.numel(), n_samples)
+            arrays["g64/" + k] = torch.cat((torch.stack((gr.sum(), gr.abs().sum(), gr.abs().max())), gr[idx]))
+            gmax = float(gr.abs().max())
+            if gmax > 1e-5:
+                worst[k] = float((torch.as_tensor(arrays["g/" + k])[3:] - gr[idx]).abs().max()) / gmax
+        top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
+        print(name, "fp32 reference vs fp64 reference, largest sampled deviations / max|g|:",
+              ", ".join("%s %.1e" % kv for kv in top))
     print(name, "loss", float(loss))
     save(name, **arrays)
 
@@ -318,7 +341,7 @@ if __name__ == "__main__":
             full_infer_case("full_infer_b32_t300_s2000", 32, 300, 2000, 1234, 111, 112, 1.0)
         if "grad64" in which:    # configs[2]: teacher-forced training step B=64, T_mel=800
             grad_case("full_grad_train_b64_t150_m800", True, 64, 150, 800, 1234, 160, wscale=1.0, n_samples=1024,
-                      keep_outputs=False)
+                      keep_outputs=False, ref64=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         grad_case("grad_train_b4", True, 4, 24, 12, 1234, 60)
