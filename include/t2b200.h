@@ -278,6 +278,23 @@ typedef struct T2AmpAdamArgs {
 size_t t2_amp_adam_workspace_bytes(int64_t total_elements, int32_t n_tensors);
 int    t2_amp_adam_step(const T2AmpAdamArgs* a, void* stream);
 
+/* ---- Tacotron2Loss fused with the parse_output mask and the gradient seeds (loss_function.py:8-19, model.py:487-497) ----
+ * mel / mel_post (B, C, T) contiguous fp32, gate (B, T), targets of the same shapes.  output_lengths (B) int32 or NULL: when
+ * given, frames t >= output_lengths[b] of mel / mel_post are zeroed and of gate set to 1e3 IN PLACE before they enter the
+ * loss (parse_output).  loss[0] = MSE(mel) + MSE(mel_post) + BCEWithLogits(gate), loss[1..3] the three terms.  d_mel /
+ * d_mel_post / d_gate (each may be NULL): d loss / d output, written in the same pass. */
+typedef struct T2LossArgs {
+  float* mel; float* mel_post; float* gate;
+  const float* mel_target; const float* gate_target;
+  const int32_t* output_lengths;
+  int32_t B, C, T;
+  float* loss;                                   /* device, 4 floats */
+  float* d_mel; float* d_mel_post; float* d_gate;
+  void* ws; size_t ws_bytes;
+} T2LossArgs;
+size_t t2_loss_workspace_bytes(void);
+int    t2_tacotron2_loss(const T2LossArgs* a, void* stream);
+
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
  * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on

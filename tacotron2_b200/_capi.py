@@ -22,6 +22,7 @@ EXPORTS = [
     "t2_encoder_stash_bytes", "t2_encoder_backward_workspace_bytes", "t2_encoder_backward",
     "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
     "t2_clip_adam_workspace_bytes", "t2_clip_adam_step", "t2_amp_adam_workspace_bytes", "t2_amp_adam_step",
+    "t2_loss_workspace_bytes", "t2_tacotron2_loss",
 ]
 
 
@@ -100,6 +101,13 @@ class T2AmpAdamArgs(C.Structure):
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class T2LossArgs(C.Structure):
+    _fields_ = [("mel", C.c_void_p), ("mel_post", C.c_void_p), ("gate", C.c_void_p), ("mel_target", C.c_void_p),
+                ("gate_target", C.c_void_p), ("output_lengths", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("T", C.c_int32),
+                ("loss", C.c_void_p), ("d_mel", C.c_void_p), ("d_mel_post", C.c_void_p), ("d_gate", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
@@ -154,6 +162,9 @@ def lib():
     L.t2_amp_adam_workspace_bytes.restype = C.c_size_t
     L.t2_amp_adam_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     L.t2_amp_adam_step.argtypes = [C.POINTER(T2AmpAdamArgs), C.c_void_p]
+    L.t2_loss_workspace_bytes.restype = C.c_size_t
+    L.t2_loss_workspace_bytes.argtypes = []
+    L.t2_tacotron2_loss.argtypes = [C.POINTER(T2LossArgs), C.c_void_p]
     L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
     L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]

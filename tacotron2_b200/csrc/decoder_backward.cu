@@ -832,7 +832,9 @@ int decoder_backward(T2Model* m, const T2DecoderBwdArgs* a, cudaStream_t s) {
     T2_LAUNCH_CHECK();
     // K = T*B*Te can exceed what one call accumulates accurately in fp32 order-wise; split per step block
     const long R = (long)TB * Te;
-    const long chunk = 1L << 20;
+    // cuBLAS cross-check: K = T*B*Te in blocks of 2^20 rows (one fp32 accumulation order per block); our GEMM drains its
+    // accumulator every 64 rows and splits K over the SMs, so it takes the whole K in one call
+    const long chunk = use_cublas_gemm() ? (1L << 20) : R;
     for (long r0 = 0; r0 < R; r0 += chunk) {
       const int k = (int)(R - r0 < chunk ? R - r0 : chunk);
       T2_TRY(gemm_rm(m, s, true, false, kAtt, kColsLd, k, w.gs + r0 * kAtt, kAtt, w.cols + r0 * kColsLd, kColsLd, w.dweff, kColsLd,

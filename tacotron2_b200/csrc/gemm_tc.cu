@@ -9,7 +9,8 @@
 // magnitude, fp16 does not), splits x = hi + lo into two fp16 planes and writes them as K-major SWIZZLE_128B operand
 // images into shared memory (double buffered).  One thread issues hi.hi + lo.hi + hi.lo per 16-wide K step into a
 // 128 x 128 fp32 accumulator in tensor memory.  Long accumulation chains in TMEM lose accuracy, so
-// every kDrain K chunks the accumulator is drained into fp32 registers (64 per thread) and restarted.  Small-tile /
+// every K chunk is its own chain (hi.hi and the cross terms in separate accumulators), drained into fp32 registers
+// (64 per thread) while the tensor pipe works on the next chunk.  Small-tile /
 // large-K shapes (the time-batched weight gradients: K = T x B = 51,200) are split along K over CTAs; the partial tiles
 // are added in a fixed order by a reduce kernel (bit-reproducible).
 #include <stdlib.h>
@@ -26,8 +27,6 @@ constexpr int kBM = 128, kBN = 128, kBK = 64;
 constexpr int kThreadsG = 256;
 constexpr int kPlane = 128 * 128;                 // one fp16 plane of 128 rows x 64 k = 16 KiB
 constexpr int kBufBytes = 4 * kPlane;             // [A hi | A lo | B hi | B lo]
-constexpr int kDrain = 16;                        // K chunks (x 12 MMAs) per TMEM accumulation chain
-constexpr int kTmemColsG = 128;
 constexpr int kTargetExp = 13;                    // scaled row / column maximum in [2^13, 2^14)
 
 // ---- pre-pass: largest magnitude of every row of op(A) / column of op(B) over K (as raw float bits, atomicMax) ------
@@ -80,73 +79,104 @@ struct GemmP {
   float beta;
 };
 
-// tile of op(X) rows [r0, r0 + 128) x k [k0, k0 + 64) -> hi / lo operand planes.  `kc`: the K dimension is contiguous
-// in memory (element (r, k) at X[r * ld + k]); otherwise the row dimension is (element at X[k * ld + r]).
-__device__ __forceinline__ void load_tile(const float* __restrict__ X, long ld, bool kc, int r0, int k0, int R, int K,
-                                          const unsigned int* __restrict__ rmax, __half* __restrict__ hi,
-                                          __half* __restrict__ lo) {
+// ---- operand tiles: global fp32 -> registers -> (transposing stage) -> split-fp16 SWIZZLE_128B planes -----------------
+// Every thread owns 4 groups of 8 consecutive elements of the 128 x 64 tile.  `kc`: the K dimension is contiguous in
+// memory (element (r, k) at X[r * ld + k]): group = 8 consecutive k of one row.  Otherwise the row dimension is
+// contiguous (element at X[k * ld + r]): group = 8 consecutive rows at one k, and the tile is transposed through a
+// padded fp32 staging tile in shared memory (conflict-free both ways) instead of scattered 2-byte stores.
+constexpr int kStagePitch = 132;                                   // floats per k-row of the staging tile (128 + 4)
+constexpr int kStageBytesG = kBK * kStagePitch * 4;                // 33,792 B
+
+__device__ __forceinline__ void load8(const float* __restrict__ src, bool vec, int n_valid, float (&v)[8]) {
+  if (vec) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (e < n_valid) ? __ldg(src + e) : 0.f;
+  }
+}
+// issue the global loads of one operand tile (no dependent instruction: all 4 x 32 B per thread are in flight together)
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ X, long ld, bool kc, int r0, int k0, int R, int K,
+                                           float (&v)[4][8]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int item = tid + q * kThreadsG;
+    if (kc) {
+      const int r = item >> 3, g8 = item & 7, row = r0 + r, k = k0 + g8 * 8;
+      if (row < R && k < K) {
+        const float* src = X + (long)row * ld + k;
+        load8(src, k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), K - k, v[q]);
+        continue;
+      }
+    } else {
+      const int kk = item >> 4, mg = item & 15, k = k0 + kk, row = r0 + mg * 8;
+      if (k < K && row < R) {
+        const float* src = X + (long)k * ld + row;
+        load8(src, row + 8 <= R && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), R - row, v[q]);
+        continue;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+  }
+}
+// registers -> scaled split-fp16 planes.  The transposing path needs two CTA-wide barriers (stage written / stage read).
+__device__ __forceinline__ void tile_store(const float (&v)[4][8], bool kc, int r0, int R, const unsigned int* __restrict__ rmax,
+                                           float* __restrict__ stage, __half* __restrict__ hi, __half* __restrict__ lo) {
   const int tid = threadIdx.x;
   if (kc) {
-#pragma unroll 1
-    for (int item = tid; item < 128 * 8; item += kThreadsG) {
-      const int r = item >> 3, g8 = item & 7, row = r0 + r, k = k0 + g8 * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int item = tid + q * kThreadsG, r = item >> 3, g8 = item & 7;
+      const float sc = (r0 + r < R) ? scale_of(rmax[r0 + r]) : 1.f;
       __align__(16) __half hh[8];
       __align__(16) __half ll[8];
-      float v[8];
-      if (row < R) {
-        const float sc = scale_of(rmax[row]);
-        const float* src = X + (long)row * ld + k;
-        if (k + 8 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (k + e < K) ? __ldg(src + e) : 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_fp16(v[e] * sc, hh[e], ll[e]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { hh[e] = __float2half(0.f); ll[e] = hh[e]; }
-      }
+      for (int e = 0; e < 8; ++e) split_fp16(v[q][e] * sc, hh[e], ll[e]);
       const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((g8 ^ (r & 7)) * 8));
       *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(hh);
       *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(ll);
     }
   } else {
-#pragma unroll 1
-    for (int item = tid; item < 64 * 16; item += kThreadsG) {
-      const int kk = item >> 4, mg = item & 15, k = k0 + kk, rb = mg * 8, row = r0 + rb;
-      float v[8];
-      if (k < K && row < R) {
-        const float* src = X + (long)k * ld + row;
-        if (row + 8 <= R && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (row + e < R) ? __ldg(src + e) : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {             // rows rb .. rb + 7 = one 8-row atom, same k
-        const float sc = (row + e < R) ? scale_of(rmax[row + e]) : 1.f;
-        __half h, l;
-        split_fp16(v[e] * sc, h, l);
-        const uint32_t off = (uint32_t)((rb >> 3) * 512 + e * 64 + ((((kk >> 3) ^ e) & 7) * 8) + (kk & 7));
-        hi[off] = h; lo[off] = l;
-      }
+    for (int q = 0; q < 4; ++q) {
+      const int item = tid + q * kThreadsG, kk = item >> 4, mg = item & 15;
+      float* d = stage + kk * kStagePitch + mg * 8;
+      *reinterpret_cast<float4*>(d) = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(v[q][4], v[q][5], v[q][6], v[q][7]);
     }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int item = tid + q * kThreadsG, r = item & 127, g8 = item >> 7;       // lanes along the rows: conflict-free reads
+      const float sc = (r0 + r < R) ? scale_of(rmax[r0 + r]) : 1.f;
+      __align__(16) __half hh[8];
+      __align__(16) __half ll[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_fp16(stage[(g8 * 8 + e) * kStagePitch + r] * sc, hh[e], ll[e]);
+      const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((g8 ^ (r & 7)) * 8));
+      *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(hh);
+      *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(ll);
+    }
+    __syncthreads();                        // the stage may be overwritten by the next operand
   }
 }
 
+// Shared memory: [2 operand buffers x 64 KiB][transposing stage 33 KiB][mbarriers, TMEM slot]; the epilogue's output tile
+// reuses the operand buffers.  TMEM: 4 accumulators of 128 columns, [chunk parity][hi.hi | cross terms]: one accumulation
+// chain = ONE K chunk (4 hi.hi MMAs in one accumulator, 8 cross-term MMAs in the other), drained into fp32 registers two
+// chunks later while the tensor pipe works on the other parity -- the tensor core's accumulator update truncates, so the
+// error grows with the chain length: 4 / 8 accumulations per chain keep the result at fp32 sgemm quality (~1e-7).
+constexpr int kTmemColsG = 512;
+constexpr int kSmemG = 2 * kBufBytes + kStageBytesG + 256;
+
 __global__ void __launch_bounds__(kThreadsG, 1) gemm_tc_kernel(const GemmP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * kBufBytes);
-  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem_raw + 2 * kBufBytes + 64);
+  float* stage = reinterpret_cast<float*>(smem_raw + 2 * kBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * kBufBytes + kStageBytesG);
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem_raw + 2 * kBufBytes + kStageBytesG + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bz = blockIdx.z, batch = bz / p.splits, split = bz - batch * p.splits;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
@@ -154,6 +184,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_tc_kernel(const GemmP p) {
   const float* B = p.B + (long)batch * p.sB;
   const int nchunks = (p.K + kBK - 1) / kBK;
   const int c0 = split * p.chunks_per_split, c1 = min(nchunks, c0 + p.chunks_per_split);
+  const bool a_kc = !p.ta, b_kc = p.tb != 0;
 
   if (tid == 0) { ptx::mbar_init(&bars[0], 1); ptx::mbar_init(&bars[1], 1); ptx::fence_barrier_init(); }
   if (warp == 0) ptx::tmem_alloc<kTmemColsG>(&tmem_slot);
@@ -167,78 +198,101 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_tc_kernel(const GemmP p) {
 #pragma unroll
   for (int i = 0; i < 64; ++i) acc[i] = 0.f;
 
-  auto drain = [&](int it_last) {            // wait for every MMA issued so far, add the accumulator to the registers
-    const int buf = it_last & 1;
-    const uint32_t parity = (uint32_t)((it_last >> 1) & 1);
-    while (!ptx::mbar_try_wait(&bars[buf], parity)) {}
+  // adds the two accumulators of chain `it` (chunk parity it & 1) to the registers, after its MMAs completed
+  auto drain = [&](int it) {
+    const int par = it & 1;
+    while (!ptx::mbar_try_wait(&bars[par], (uint32_t)((it >> 1) & 1))) {}
     ptx::tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 64; c += 8) {
-      float g[8];
-      ptx::tmem_ld8(t_lane + c, g);
+      float g[8], h[8];
+      ptx::tmem_ld8(t_lane + (uint32_t)(par * 256) + c, g);
+      ptx::tmem_ld8(t_lane + (uint32_t)(par * 256 + 128) + c, h);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[c + i] += g[i];
+      for (int i = 0; i < 8; ++i) acc[c + i] += g[i] + h[i];
     }
     ptx::tc_fence_before();
-    __syncthreads();
   };
 
-  int it = 0, in_chain = 0;
+  int it = 0;
   for (int c = c0; c < c1; ++c, ++it) {
     const int buf = it & 1;
     uint8_t* sb = smem_raw + buf * kBufBytes;
-    if (it >= 2) {                          // the MMAs that read this buffer two chunks ago are complete
-      const uint32_t parity = (uint32_t)(((it >> 1) - 1) & 1);
-      while (!ptx::mbar_try_wait(&bars[buf], parity)) {}
-    }
-    load_tile(A, p.lda, !p.ta, m0, c * kBK, p.M, p.K, p.amax, reinterpret_cast<__half*>(sb), reinterpret_cast<__half*>(sb + kPlane));
-    load_tile(B, p.ldb, p.tb != 0, n0, c * kBK, p.N, p.K, p.bmax, reinterpret_cast<__half*>(sb + 2 * kPlane),
-              reinterpret_cast<__half*>(sb + 3 * kPlane));
+    float va[4][8], vb[4][8];
+    tile_fetch(A, p.lda, a_kc, m0, c * kBK, p.M, p.K, va);         // both operands' loads in flight during the drain below
+    tile_fetch(B, p.ldb, b_kc, n0, c * kBK, p.N, p.K, vb);
+    if (it >= 2) drain(it - 2);             // chain it-2 read this operand buffer and wrote this accumulator parity
+    tile_store(va, a_kc, m0, p.M, p.amax, stage, reinterpret_cast<__half*>(sb), reinterpret_cast<__half*>(sb + kPlane));
+    tile_store(vb, b_kc, n0, p.N, p.bmax, stage, reinterpret_cast<__half*>(sb + 2 * kPlane), reinterpret_cast<__half*>(sb + 3 * kPlane));
     ptx::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       ptx::tc_fence_after();
       const uint32_t a_hi = ptx::smem_u32(sb), a_lo = a_hi + kPlane, b_hi = a_hi + 2 * kPlane, b_lo = a_hi + 3 * kPlane;
       const uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+      const uint32_t d_hh = tmem + (uint32_t)(buf * 256), d_x = d_hh + 128;
 #pragma unroll
       for (int kk = 0; kk < kBK / 16; ++kk) {
         const uint64_t dah = ptx::make_sw128_desc(a_hi + kk * 32), dal = ptx::make_sw128_desc(a_lo + kk * 32);
         const uint64_t dbh = ptx::make_sw128_desc(b_hi + kk * 32), dbl = ptx::make_sw128_desc(b_lo + kk * 32);
-        ptx::umma_f16(tmem, dah, dbh, idesc, (in_chain > 0 || kk > 0) ? 1u : 0u);
-        ptx::umma_f16(tmem, dal, dbh, idesc, 1u);
-        ptx::umma_f16(tmem, dah, dbl, idesc, 1u);
+        ptx::umma_f16(d_hh, dah, dbh, idesc, kk > 0 ? 1u : 0u);
+        ptx::umma_f16(d_x, dal, dbh, idesc, kk > 0 ? 1u : 0u);
+        ptx::umma_f16(d_x, dah, dbl, idesc, 1u);
       }
       ptx::umma_commit(&bars[buf]);
     }
-    ++in_chain;
-    if (in_chain == kDrain || c + 1 == c1) { drain(it); in_chain = 0; }
   }
+  if (it >= 2) drain(it - 2);
+  if (it >= 1) drain(it - 1);
+  __syncthreads();                          // every MMA is complete: the operand buffers become the output tile
 
-  // ---- epilogue: undo the scales, write C (or the partial tile of this K split) --------------------------------
-  const int m = m0 + quad * 32 + lane;
-  if (m < p.M) {
-    const float ia = 1.f / scale_of(p.amax[m]);
-    if (p.part) {
-      float* dst = p.part + (((long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (kBM * kBN) +
-                   (long)(quad * 32 + lane) * kBN + chalf * 64;
+  // ---- epilogue: undo the scales, transpose through shared memory, coalesced stores -----------------------------------
+  float* tile = reinterpret_cast<float*>(smem_raw);                 // [128][kStagePitch]
+  {
+    const int r = quad * 32 + lane, m = m0 + r;
+    const float ia = (m < p.M) ? 1.f / scale_of(p.amax[m]) : 0.f;
+    float* trow = tile + r * kStagePitch + chalf * 64;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        float4 v;
-        v.x = acc[j + 0] * (ia / scale_of(n0 + chalf * 64 + j + 0 < p.N ? p.bmax[n0 + chalf * 64 + j + 0] : 0u));
-        v.y = acc[j + 1] * (ia / scale_of(n0 + chalf * 64 + j + 1 < p.N ? p.bmax[n0 + chalf * 64 + j + 1] : 0u));
-        v.z = acc[j + 2] * (ia / scale_of(n0 + chalf * 64 + j + 2 < p.N ? p.bmax[n0 + chalf * 64 + j + 2] : 0u));
-        v.w = acc[j + 3] * (ia / scale_of(n0 + chalf * 64 + j + 3 < p.N ? p.bmax[n0 + chalf * 64 + j + 3] : 0u));
-        *reinterpret_cast<float4*>(dst + j) = v;
+    for (int j = 0; j < 64; j += 4) {
+      const int n = n0 + chalf * 64 + j;
+      float4 v;
+      v.x = acc[j + 0] * (ia / scale_of(n + 0 < p.N ? p.bmax[n + 0] : 0u));
+      v.y = acc[j + 1] * (ia / scale_of(n + 1 < p.N ? p.bmax[n + 1] : 0u));
+      v.z = acc[j + 2] * (ia / scale_of(n + 2 < p.N ? p.bmax[n + 2] : 0u));
+      v.w = acc[j + 3] * (ia / scale_of(n + 3 < p.N ? p.bmax[n + 3] : 0u));
+      *reinterpret_cast<float4*>(trow + j) = v;
+    }
+  }
+  __syncthreads();
+  if (p.part) {                             // partial tile of this K split: contiguous 128 x 128
+    float* dst = p.part + (((long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (long)(kBM * kBN);
+    for (int idx = tid; idx < kBM * (kBN / 4); idx += kThreadsG) {
+      const int r = idx >> 5, c4 = idx & 31;
+      *reinterpret_cast<float4*>(dst + r * kBN + c4 * 4) = *reinterpret_cast<const float4*>(tile + r * kStagePitch + c4 * 4);
+    }
+  } else {
+    float* Cb = p.C + (long)batch * p.sC;
+    const bool vec = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && n0 + kBN <= p.N;
+    if (vec) {
+      for (int idx = tid; idx < kBM * (kBN / 4); idx += kThreadsG) {
+        const int r = idx >> 5, c4 = idx & 31, m = m0 + r;
+        if (m >= p.M) continue;
+        float4 v = *reinterpret_cast<const float4*>(tile + r * kStagePitch + c4 * 4);
+        float4* dst = reinterpret_cast<float4*>(Cb + (long)m * p.ldc + n0 + c4 * 4);
+        if (p.beta != 0.f) {
+          const float4 o = *dst;
+          v.x = fmaf(p.beta, o.x, v.x); v.y = fmaf(p.beta, o.y, v.y); v.z = fmaf(p.beta, o.z, v.z); v.w = fmaf(p.beta, o.w, v.w);
+        }
+        *dst = v;
       }
     } else {
-      float* crow = p.C + (long)batch * p.sC + (long)m * p.ldc;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int n = n0 + chalf * 64 + j;
-        if (n < p.N) {
-          const float v = acc[j] * (ia / scale_of(p.bmax[n]));
-          crow[n] = p.beta != 0.f ? fmaf(p.beta, crow[n], v) : v;
-        }
+      for (int idx = tid; idx < kBM * kBN; idx += kThreadsG) {
+        const int r = idx >> 7, cidx = idx & 127, m = m0 + r, n = n0 + cidx;
+        if (m >= p.M || n >= p.N) continue;
+        float v = tile[r * kStagePitch + cidx];
+        float* dst = Cb + (long)m * p.ldc + n;
+        if (p.beta != 0.f) v = fmaf(p.beta, *dst, v);
+        *dst = v;
       }
     }
   }
@@ -319,10 +373,9 @@ int gemm_tc(T2Model* m, cudaStream_t s, const GemmTc& g) {
   const int ntm = (g.M + kBM - 1) / kBM, ntn = (g.N + kBN - 1) / kBN, nchunks = (g.K + kBK - 1) / kBK;
   const long tiles = (long)ntm * ntn * batch;
   int splits = 1;
-  if (tiles < 120 && nchunks >= 8) {
-    splits = (int)((296 + tiles - 1) / tiles);
+  if (tiles < 120 && nchunks >= 8) {         // fill one wave of CTAs (1 CTA / SM: 161 KiB of shared memory)
+    splits = tiles <= 74 ? (int)(148 / tiles) : 2;
     if (splits > nchunks / 4) splits = nchunks / 4;
-    if (splits > 128) splits = 128;
     if (splits < 1) splits = 1;
   }
   const int cps = (nchunks + splits - 1) / splits;
@@ -340,7 +393,9 @@ int gemm_tc(T2Model* m, cudaStream_t s, const GemmTc& g) {
   for (int b = 0; b < batch; ++b) {
     const float* A = g.A + (long)b * g.strideA;
     const float* B = g.B + (long)b * g.strideB;
-    const int ysp = g.K >= 4096 ? 32 : (g.K >= 512 ? 4 : 1);
+    // K splits of the maximum search: enough blocks to saturate HBM on the long-K operands (K up to 7.7 M rows)
+    int ysp = g.K >= 4096 ? 32 : (g.K >= 512 ? 4 : 1);
+    if (g.K >= (1 << 16)) { ysp = g.K >> 9; if (ysp > 1024) ysp = 1024; }
     if (!g.ta) absmax_inner_contig_kernel<<<dim3((g.M + 7) / 8, ysp), dim3(32, 8), 0, s>>>(A, g.lda, g.M, g.K, amax);
     else absmax_outer_contig_kernel<<<dim3((g.M + 31) / 32, ysp), dim3(32, 8), 0, s>>>(A, g.lda, g.M, g.K, amax);
     T2_LAUNCH_CHECK();
@@ -356,7 +411,7 @@ int gemm_tc(T2Model* m, cudaStream_t s, const GemmTc& g) {
   p.M = g.M; p.N = g.N; p.K = g.K; p.ta = g.ta ? 1 : 0; p.tb = g.tb ? 1 : 0; p.splits = splits; p.chunks_per_split = cps;
   p.batch = batch; p.beta = g.beta;
   static bool attr_set = false;
-  const size_t smem = 2 * (size_t)kBufBytes + 1024;
+  const size_t smem = (size_t)kSmemG;
   if (!attr_set) {
     T2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;

@@ -339,8 +339,8 @@ def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
         gt[i, n - 1:] = 1
     m = dict(pk=keep_mask((Tm + 1, 2, B, 256), 0.5, 1), ak=keep_mask((Tm, B, 1024), 0.1, 2), dk=keep_mask((Tm, B, 1024), 0.1, 3),
              ek=keep_mask((3, B, 512, Tt), 0.5, 4), qk4=keep_mask((4, B, 512, Tm), 0.5, 5), qk1=keep_mask((B, 80, Tm), 0.5, 6))
-    ref_loss, _, ref_g32 = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
-    _, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, True, dtype=torch.float64)
+    ref_loss32, _, ref_g32 = oracle_train_step(sd, text, tl, ol, mels, gt, m, True)
+    ref_loss, _, ref_g = oracle_train_step(sd, text, tl, ol, mels, gt, m, True, dtype=torch.float64)
     model = t2.Tacotron2(t2.create_hparams())
     model.load_state_dict(sd)
     model = model.cuda().train()
@@ -350,7 +350,9 @@ def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
         loss = t2.Tacotron2Loss()(out, (mels.cuda(), gt.cuda()))
         loss.backward()
     torch.cuda.synchronize()
-    assert abs(loss.item() - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    # the loss too: five stacked BatchNorms over 1-2 frames per channel move it by 2e-4 between fp32 and fp64 alone
+    loss_yard = abs(float(ref_loss32) - float(ref_loss)) / abs(float(ref_loss))
+    assert abs(loss.item() - float(ref_loss)) < max(1e-4, 8.0 * loss_yard) * abs(float(ref_loss)), (loss.item(), float(ref_loss), loss_yard)
     gmax = max(float(v.abs().max()) for v in ref_g.values())
     errs, yard = {}, {}
     for k, p in model.named_parameters():
@@ -363,3 +365,44 @@ def test_train_step_minimal_shapes_vs_oracle_autograd(B, Tt, Tm):
           "oracle: %.2e)" % (B, Tt, Tm, loss.item(), max(errs.values()), max(yard.values())))
     bad = {k: (v, yard[k]) for k, v in errs.items() if not v < max(1e-3, 8.0 * yard[k])}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 37), (64, 800)])
+def test_fused_loss_and_gradient_seeds_vs_oracle(B, T):
+    """t2_tacotron2_loss: Tacotron2Loss + its gradient seeds in one pass vs oracle.tacotron2_loss and
+    torch autograd; and the in-place parse_output mask (model.py:487-497) when output_lengths is handed to the kernel."""
+    import ctypes as C
+    from tacotron2_b200 import _capi
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    mel, post = torch.randn(B, 80, T, generator=g), torch.randn(B, 80, T, generator=g)
+    gate = torch.randn(B, T, generator=g) * 3
+    tgt = torch.randn(B, 80, T, generator=g)
+    gt = (torch.rand(B, T, generator=g) > 0.7).float()
+    lens = torch.randint(1, T + 1, (B,), generator=g); lens[0] = T
+    # (a) through the nn.Module: loss value and gradients
+    leaves = [x.clone().requires_grad_(True) for x in (mel, post, gate)]
+    ref = O.tacotron2_loss(leaves[0], leaves[1], leaves[2], tgt, gt)
+    ref.backward()
+    dev = [x.clone().cuda().requires_grad_(True) for x in (mel, post, gate)]
+    loss = t2.Tacotron2Loss()([dev[0], dev[1], dev[2], None], (tgt.cuda(), gt.cuda()))
+    (loss * 3.0).backward()
+    assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref))
+    for a, b in zip(dev, leaves):
+        assert rel_err(a.grad, 3.0 * b.grad) < 1e-5
+    # (b) the C entry point with output_lengths: masks in place, then the same loss as masking first
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    ref_m = O.tacotron2_loss(mel.masked_fill(pad[:, None, :], 0.0), post.masked_fill(pad[:, None, :], 0.0),
+                             gate.masked_fill(pad, 1e3), tgt, gt)
+    L = _capi.lib()
+    m_d, p_d, g_d, t_d, gt_d = (x.clone().cuda().contiguous() for x in (mel, post, gate, tgt, gt))
+    l32 = lens.to(torch.int32).cuda()
+    out = torch.empty(4, device="cuda")
+    ws = torch.empty(int(L.t2_loss_workspace_bytes()), dtype=torch.uint8, device="cuda")
+    a = _capi.T2LossArgs()
+    a.mel, a.mel_post, a.gate, a.mel_target, a.gate_target = (x.data_ptr() for x in (m_d, p_d, g_d, t_d, gt_d))
+    a.output_lengths, a.B, a.C, a.T, a.loss = l32.data_ptr(), B, 80, T, out.data_ptr()
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+    _capi.check(L.t2_tacotron2_loss(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert abs(float(out[0]) - float(ref_m)) < 2e-6 * abs(float(ref_m))
+    assert torch.equal(m_d.cpu(), mel.masked_fill(pad[:, None, :], 0.0)) and torch.equal(g_d.cpu(), gate.masked_fill(pad, 1e3))
