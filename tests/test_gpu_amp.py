@@ -147,7 +147,6 @@ def test_o2_training_step_matches_oracle_with_the_same_rounding_points():
     _, _, _, g16_j = emulate(_Round16Jitter.apply)
     assert abs(float(loss) - float(ref_loss)) < 2e-4 * abs(float(ref_loss))
     assert rel_err(out[0], mel_m) < 1e-3 and rel_err(out[1], post_m) < 1e-3
-    g16 = {k: (sdg[k].grad if is_bn(k) else sdg[k].grad.half().float()) for k in names}     # fp16 gradient storage
     errs = {}
     for k in names:
         gmax = float(g16[k].abs().max())
