@@ -316,6 +316,9 @@ int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32
 /* Micro-benchmark: SM cycles for `reps` back-to-back tcgen05.mma (M x N x 16, fp16, operands resident in
  * shared memory) -> out_host[0] = issue cycles, out_host[1] = issue + completion cycles. */
 int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host);
+/* `reps` groups of `group` back-to-back MMAs, each group followed by tcgen05.commit + a wait for it (one K chunk of a
+ * streaming event): out_host[0] = total SM cycles. */
+int t2_selftest_mma_group(int32_t M, int32_t N, int32_t group, int32_t reps, int64_t* out_host);
 /* The training path's general tensor-core GEMM (gemm_tc.cu): row-major C = op(A) . op(B) + beta C, strided batch. */
 int t2_selftest_gemm_tc(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
                         const float* B, int64_t ldb, float* C, int64_t ldc, float beta, int32_t batch,

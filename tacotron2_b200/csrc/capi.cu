@@ -34,6 +34,7 @@ int postnet_forward(T2Model* m, const T2PostnetArgs* a, cudaStream_t s);
 size_t postnet_ws_bytes(int B, int T);
 int selftest_umma(const float* A, const float* W, int N, int K, int passes, float* C, cudaStream_t s);
 int mma_rate(int M, int N, int reps, int alternate_d, long long* out_host, cudaStream_t s);
+int mma_group(int M, int N, int group, int reps, long long* out_host, cudaStream_t s);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -393,6 +394,10 @@ int t2_decoder_profile(const T2DecoderArgs* a, int64_t* out_host) {
 #ifdef T2_SELFTEST   // libt2b200_selftest.so only
 int t2_selftest_mma_rate(int32_t M, int32_t N, int32_t reps, int32_t alternate_d, int64_t* out_host) {
   return mma_rate(M, N, reps, alternate_d, (long long*)out_host, 0);
+}
+
+int t2_selftest_mma_group(int32_t M, int32_t N, int32_t group, int32_t reps, int64_t* out_host) {
+  return mma_group(M, N, group, reps, (long long*)out_host, 0);
 }
 
 int t2_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t passes, float* C, void* stream) {

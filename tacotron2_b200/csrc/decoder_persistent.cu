@@ -365,7 +365,13 @@ __device__ __forceinline__ void prefetch_weights(Ring& rg, const EventPlan& nx, 
 // complete.  Every MMA accumulates (the epilogues zero what they consume).
 __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const uint8_t* x_img,
                                           const uint8_t* w_img, int chunks, uint32_t tmem_base,
-                                          DecoderCtrl* ctrl, const EventPlan* next) {
+                                          DecoderCtrl* ctrl, const EventPlan* next,
+                                          const unsigned int* ready = nullptr, unsigned int ready_target = 0) {
+  // ready (16 counters, one per K chunk of the activation; null = the caller synchronised already): chunk i of x_img is
+  // complete once ready[i] >= ready_target.  The activation blocks ah / dh are written in 8-column slices by 128 CTAs, i.e.
+  // a 64-column chunk has 8 producers: instead of a 128-way barrier between the epilogue that writes a block and the event
+  // that streams it, the bulk-copy producer fetches a chunk as soon as ITS 8 producers have arrived, so the stragglers'
+  // skew and the arrival latency overlap with the streaming of the chunks that are already there.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (ep.nrows == 0) {                 // this CTA (and its whole cluster) has no consumer of this activation
     if (threadIdx.x == 0 && next != nullptr && next->nrows != 0 && rg.pre == 0) prefetch_weights(rg, *next, w_img, ctrl);
@@ -373,6 +379,7 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
   }
   if (warp == 0) {
     if (lane == 0) {
+      int nready = ready ? 0 : chunks;     // chunks [0, nready) are known to be complete
       for (int i = 0; i < chunks; ++i) {
         uint8_t* st = rg.stage(rg.p_stage);
         if ((uint32_t)i >= rg.pre) {     // not armed / issued ahead of time
@@ -380,6 +387,24 @@ __device__ __forceinline__ void run_event(Ring& rg, const EventPlan& ep, const u
           ptx::mbar_arrive_expect_tx(&rg.full[rg.p_stage], kXChunkBytes + ep.w_bytes);
           ptx::bulk_g2s_hint(st + kXChunkBytes, w_img + ep.w_off + (size_t)i * ep.w_bytes, ep.w_bytes,
                              &rg.full[rg.p_stage], rg.pol_w);
+        }
+        if (i >= nready) {               // all 16 counters in one round trip; take the leading run of complete chunks
+          const unsigned long long t0 = clock64();
+          while (true) {
+            uint32_t c[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(c[j]), "=r"(c[j + 1]), "=r"(c[j + 2]), "=r"(c[j + 3]) : "l"(ready + j) : "memory");
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mask |= ((int)(c[j] - ready_target) >= 0 ? 1u : 0u) << j;
+            const int run = __ffs((int)~(mask >> i)) - 1;          // complete chunks starting at i
+            if (run > 0) { nready = min(chunks, i + run); break; }
+            if (clock64() - t0 > kWatchdogCycles) watchdog_trap(ctrl, 206);
+          }
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          ptx::fence_proxy_async();
         }
         if (rg.cs == 1) {
           ptx::bulk_g2s_hint(st, x_img + (size_t)i * kXChunkBytes, kXChunkBytes, &rg.full[rg.p_stage], rg.pol_x);
@@ -482,6 +507,7 @@ struct KParams {
   DecoderCtrl* ctrl;
   int B, T, cap, infer, training, cluster, hier_barrier;
   int nstages;                      // operand ring stages (4 or 5)
+  int chunk_ready;                  // 1: ah / dh hand-over through per-chunk arrival counters instead of barriers B1 / B4
   int b0, Btot;                     // this launch handles batch rows [b0, b0 + B) of Btot (dropout mask / Philox indexing)
   float gate_threshold, score_mask_value, p_att, p_dec;
   uint64_t seed;
@@ -675,7 +701,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (p.st.ga) stash_lstm(p.st.ga, p.st.ca, p.st.ha, t, p.Btot, p.b0 + row, cta * 8 + cg * 2, sg, c_att, hv);
       }
       T2_PROF(1);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B1: ah_t complete
+      if (p.chunk_ready) signal_counter(&ctrl->ah_count[cta >> 3], 1u);                        // this CTA's 8 columns of ah_t are written
+      else grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                     // B1: ah_t complete
       T2_PROF(2);
     }
     // ======== E1: ah_t -> dec gates (part), next att gates (part), query ===== model.py:57, 366-369
@@ -705,7 +732,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         }
         s_mask[row] = bits;
       }
-      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr);   // the attention phase reuses the ring as scratch
+      run_event(rg, plan.ev[1], p.ah_img, p.wimg, 16, tmem_base, ctrl, nullptr,    // the attention phase reuses the ring as scratch
+                p.chunk_ready ? ctrl->ah_count : nullptr, 8u * (unsigned int)(t + 1));
       if (has_q) {
         float g[8];
         if (cg == 0) acc_take8(t_lane, kColS, kNS, 0, g);
@@ -959,13 +987,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
         if (p.st.ga) stash_lstm(p.st.gd, p.st.cd, p.st.hd, t, p.Btot, p.b0 + row, cta * 8 + cg * 2, sg, c_dec, hv);
       }
       T2_PROF(8);
-      grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                          // B4: dh_t complete
+      if (p.chunk_ready) signal_counter(&ctrl->dh_count[cta >> 3], 1u);                        // this CTA's 8 columns of dh_t are written
+      else grid_barrier(ctrl, bar_target, bar_cs, rg.rank);                                     // B4: dh_t complete
       T2_PROF(9);
     }
     // ======== E3: dh_t -> projection (rest), next dec gates (part); epilogue -> mel, gate, x1
     {
       run_event(rg, plan.ev[3], p.dh_img, p.wimg, 16, tmem_base, ctrl,
-                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr);   // INFER: the loop may end after this step
+                (!p.infer && t + 1 < p.cap) ? &plan.ev[0] : nullptr,    // INFER: the loop may end after this step
+                p.chunk_ready ? ctrl->dh_count : nullptr, 8u * (unsigned int)(t + 1));
       T2_PROF(10);
       if (tid == 0) *s_live = 0;
       float g[8];
@@ -1267,6 +1297,10 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
   p.nstages = persistent_stages(T);
   {
   }
+  {
+    const char* e = getenv("T2_CHUNK_READY");      // "0": full grid barriers B1 / B4 (cross-check / A-B)
+    p.chunk_ready = (e && !strcmp(e, "0")) ? 0 : 1;
+  }
   const size_t smem = persistent_smem_bytes(T, p.nstages);
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   T2_CUDA(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1316,8 +1350,8 @@ static int run_persistent_slice(T2Model* m, const T2DecoderArgs* a, cudaStream_t
     le = cudaLaunchKernelEx(&cfg, decoder_persistent_kernel, p);
   }
   if (le != cudaSuccess) return fail(T2_ERR_CUDA, "persistent decoder launch failed: %s", cudaGetErrorString(le));
-  if (getenv("T2_VERBOSE")) fprintf(stderr, "[t2b200] persistent decoder: B=%d T_enc=%d cap=%d cluster=%d stages=%d smem=%zu\n",
-                                    B, T, cap, p.cluster, p.nstages, smem);
+  if (getenv("T2_VERBOSE")) fprintf(stderr, "[t2b200] persistent decoder: B=%d T_enc=%d cap=%d cluster=%d stages=%d chunk_ready=%d smem=%zu\n",
+                                    B, T, cap, p.cluster, p.nstages, p.chunk_ready, smem);
   g_launch_count++;
   return T2_OK;
 }
