@@ -199,10 +199,12 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "mel frames/sec (B=64,T_text=150)", "value": cb["value"], "unit": "mel frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD + "; reference arm: oracle port on the host CPU cores, %s per timed pass"
-                                   % ("all 800 decoder steps" if dec_steps == T_MEL else
-                                      "%d of 800 decoder steps measured, extrapolated linearly" % dec_steps),
-                       "global_batch": B_PER_GPU},
+            # same workload string as the GPU arm (the driver compares the two configs); how this arm ran it is in `arm`
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * max(args.gpus, 1),
+                       "arm": "oracle port on the host CPU cores (one host works through the %d shard(s) of 64 rows one after the "
+                              "other: its frames/s does not depend on N), %s per timed pass"
+                              % (max(args.gpus, 1), "all 800 decoder steps" if dec_steps == T_MEL else
+                                 "%d of 800 decoder steps measured, extrapolated linearly" % dec_steps)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}

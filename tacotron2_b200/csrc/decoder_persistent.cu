@@ -902,16 +902,19 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_persistent_kernel(const K
       // cross-warp exchange), then the threads split the normalised write-out
       const int len = p.mem_len ? p.mem_len[b] : T;
       const int eN = ntiles * 128;
-      auto eraw = [&](int j) { return (s_ep[j] + s_ep[eN + j]) + (s_ep[2 * eN + j] + s_ep[3 * eN + j]); };
+      // masked energies once (the four 32-dim partial sums added in a fixed order), in place in the first partial-sum plane
+      for (int j = tid; j < T; j += kThreads)
+        s_ep[j] = (j < len) ? (s_ep[j] + s_ep[eN + j]) + (s_ep[2 * eN + j] + s_ep[3 * eN + j]) : p.score_mask_value;
+      __syncthreads();
       float mx = -INFINITY;
-      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, (j < len) ? eraw(j) : p.score_mask_value);
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, s_ep[j]);
       mx = warp_max_f(mx);
       float sum = 0.f;
-      for (int j = lane; j < T; j += 32) sum += expf(((j < len) ? eraw(j) : p.score_mask_value) - mx);
+      for (int j = lane; j < T; j += 32) sum += expf(s_ep[j] - mx);
       sum = warp_sum_f(sum);
       const float inv = 1.f / sum;
       for (int j = tid; j < T; j += kThreads) {
-        const float a = expf(((j < len) ? eraw(j) : p.score_mask_value) - mx) * inv;
+        const float a = expf(s_ep[j] - mx) * inv;
         s_e[j] = a;
         s_pad0[halfk + j] = a;                                                // becomes "previous"
         s_pad1[halfk + j] += a;                                               // model.py:365

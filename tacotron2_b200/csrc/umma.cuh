@@ -147,6 +147,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, do other work, then wait (the wait names the registers so no use is scheduled before it)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+
 // registers -> TMEM: zero 8 consecutive columns of this thread's lane
 __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
   const uint32_t z = 0u;
