@@ -295,6 +295,23 @@ typedef struct T2LossArgs {
 size_t t2_loss_workspace_bytes(void);
 int    t2_tacotron2_loss(const T2LossArgs* a, void* stream);
 
+/* ---- TacotronSTFT.mel_spectrogram (layers.py:63-80, stft.py:69-94): batch of waveforms -> log-mel spectrograms ----------
+ * y (B, n_samples) fp32 in [-1, 1] (not checked here; the Python mirror asserts it like the reference does).
+ * forward_basis (2 * (filter_length / 2 + 1), filter_length): the windowed Fourier basis of stft.py:44-63;
+ * mel_basis (n_mel, filter_length / 2 + 1).  mel out: (B, n_mel, n_frames) = log(max(mel_basis . |STFT|, clip_val)),
+ * n_frames = n_samples / hop_length + 1 (reflect padding by filter_length / 2 on both sides). */
+typedef struct T2MelSpecArgs {
+  const float* y; int32_t B, n_samples;
+  int32_t filter_length, hop_length, n_mel;
+  const float* forward_basis; const float* mel_basis;
+  float clip_val;
+  float* mel;
+  void* ws; size_t ws_bytes;
+} T2MelSpecArgs;
+int32_t t2_mel_spectrogram_frames(int32_t n_samples, int32_t hop_length);
+size_t  t2_mel_spectrogram_workspace_bytes(int32_t B, int32_t n_samples, int32_t filter_length, int32_t hop_length, int32_t n_mel);
+int     t2_mel_spectrogram(const T2MelSpecArgs* a, void* stream);
+
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
  * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on

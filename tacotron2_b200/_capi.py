@@ -23,6 +23,7 @@ EXPORTS = [
     "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
     "t2_clip_adam_workspace_bytes", "t2_clip_adam_step", "t2_amp_adam_workspace_bytes", "t2_amp_adam_step",
     "t2_loss_workspace_bytes", "t2_tacotron2_loss",
+    "t2_mel_spectrogram_frames", "t2_mel_spectrogram_workspace_bytes", "t2_mel_spectrogram",
 ]
 
 
@@ -108,6 +109,12 @@ class T2LossArgs(C.Structure):
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class T2MelSpecArgs(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("B", C.c_int32), ("n_samples", C.c_int32), ("filter_length", C.c_int32),
+                ("hop_length", C.c_int32), ("n_mel", C.c_int32), ("forward_basis", C.c_void_p), ("mel_basis", C.c_void_p),
+                ("clip_val", C.c_float), ("mel", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
@@ -165,6 +172,10 @@ def lib():
     L.t2_loss_workspace_bytes.restype = C.c_size_t
     L.t2_loss_workspace_bytes.argtypes = []
     L.t2_tacotron2_loss.argtypes = [C.POINTER(T2LossArgs), C.c_void_p]
+    L.t2_mel_spectrogram_frames.argtypes = [C.c_int32, C.c_int32]
+    L.t2_mel_spectrogram_workspace_bytes.restype = C.c_size_t
+    L.t2_mel_spectrogram_workspace_bytes.argtypes = [C.c_int32] * 5
+    L.t2_mel_spectrogram.argtypes = [C.POINTER(T2MelSpecArgs), C.c_void_p]
     L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
     L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]

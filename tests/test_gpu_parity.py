@@ -288,3 +288,26 @@ def test_column_sums_kernel():
                                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     ref = X[:, :81].double().sum(0)
     assert rel_err(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("B,n,cfg", [(2, 6000, (1024, 256, 1024, 80)), (5, 22050 * 3 + 17, (1024, 256, 1024, 80)), (3, 4000, (800, 200, 800, 40))])
+def test_mel_spectrogram_vs_oracle(B, n, cfg):
+    """TacotronSTFT.mel_spectrogram on the GPU (t2_mel_spectrogram: reflect pad, windowed DFT as a strided-batch tensor-core
+    GEMM over overlapping frames, magnitude, mel projection, log) vs oracle/stft_oracle.py, whose STFT half is pinned by the
+    reference's own stft.STFT (tests/golden/stft_mag.npz); layers.py:63-80."""
+    from oracle import stft_oracle as S
+    fl, hop, win, n_mel = cfg
+    if (B, n) == (2, 6000):
+        y = torch.from_numpy(load("stft_mag")["y"])
+    else:
+        g = torch.Generator().manual_seed(n)
+        t = torch.arange(n) / 22050.0
+        y = torch.stack([(0.4 * torch.sin(2 * 3.14159265 * (110.0 * (b + 1)) * t) + 0.1 * torch.randn(n, generator=g)).clamp(-1, 1) for b in range(B)])
+    stft = t2.TacotronSTFT(fl, hop, win, n_mel_channels=n_mel).cuda()
+    got = stft.mel_spectrogram(y.cuda())
+    ref = S.mel_spectrogram(y, fl, hop, win, n_mel_channels=n_mel)
+    assert got.shape == ref.shape == (B, n_mel, n // hop + 1)
+    assert float((got.cpu() - ref).abs().max()) < 1e-3                      # log-mel, absolute
+    assert rel_err(torch.exp(got), torch.exp(ref)) < 1e-4                     # linear mel energies, relative to the maximum
+    with pytest.raises(AssertionError):
+        stft.mel_spectrogram((y * 3).cuda())                                  # layers.py:74-75 range check

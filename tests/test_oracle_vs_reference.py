@@ -81,3 +81,22 @@ def test_reference_training_step_gradients_live():
             assert float(o_grads[k].abs().max()) < 1e-4
             continue
         assert rel_err(o_grads[k], p.grad) < 1e-4, k
+
+
+def test_stft_oracle_vs_reference_stft_live():
+    """oracle/stft_oracle.py against the reference's own stft.STFT executed here (functional stand-ins for the two
+    librosa.util helpers stft.py imports): the windowed Fourier basis and the magnitudes for two filter / hop settings."""
+    import os
+    import sys
+    if not os.path.isfile("/root/reference/stft.py"):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from oracle import stft_oracle as S
+    from tools.make_golden import import_reference_stft, stft_inputs
+    mod = import_reference_stft()
+    for fl, hop, win in ((1024, 256, 1024), (800, 200, 800), (512, 128, 400)):
+        ref_stft = mod.STFT(fl, hop, win)
+        assert float((ref_stft.forward_basis[:, 0, :] - torch.from_numpy(S.stft_forward_basis(fl, win))).abs().max()) < 1e-6
+        y = stft_inputs(seed=fl, n=5000)
+        mag, _ = ref_stft.transform(y)
+        assert rel_err(S.stft_magnitude(y, fl, hop, win), mag) < 1e-6

@@ -332,7 +332,57 @@ def grad_case(name, training, B, T_text, T_mel, wseed, seed, wscale=2.0, n_sampl
     save(name, **arrays)
 
 
+def import_reference_stft():
+    """The reference's stft.py with functional stand-ins for the two librosa.util helpers it imports (librosa itself is
+    not in this image): pad_center = symmetric zero padding, tiny = smallest normal float32."""
+    import importlib.util
+    import types
+
+    def pad_center(data, size, axis=-1, **kw):
+        n = data.shape[axis]
+        lpad = int((size - n) // 2)
+        lengths = [(0, 0)] * data.ndim
+        lengths[axis] = (lpad, int(size - n - lpad))
+        return np.pad(data, lengths, mode="constant")
+    saved = {k: sys.modules.get(k) for k in ("librosa", "librosa.util", "librosa.filters", "audio_processing", "stft")}
+    lib, lu, lf = types.ModuleType("librosa"), types.ModuleType("librosa.util"), types.ModuleType("librosa.filters")
+    lu.pad_center, lu.tiny, lf.mel = pad_center, (lambda x: np.finfo(np.float32).tiny), None
+    lib.util, lib.filters = lu, lf
+    sys.modules.update({"librosa": lib, "librosa.util": lu, "librosa.filters": lf})
+    sys.path.insert(0, "/root/reference")
+    try:
+        spec = importlib.util.spec_from_file_location("t2_reference_stft", "/root/reference/stft.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove("/root/reference")
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+    return mod
+
+
+def stft_inputs(seed=0, n=6000):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n) / 22050.0
+    return torch.stack([0.3 * torch.sin(2 * np.pi * 220 * t) + 0.2 * torch.sin(2 * np.pi * 1870 * t) + 0.05 * torch.randn(n, generator=g),
+                        (0.5 * torch.randn(n, generator=g)).clamp(-1, 1)])
+
+
+def stft_case():
+    """STFT magnitudes of the reference's own stft.STFT(1024, 256, 1024) (stft.py:69-94) for a seeded 2-row signal."""
+    mod = import_reference_stft()
+    ref_stft = mod.STFT(1024, 256, 1024)
+    y = stft_inputs()
+    mag, _ = ref_stft.transform(y)
+    save("stft_mag", y=y, mag=mag, basis_abs_sum=ref_stft.forward_basis.double().abs().sum())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "stft":
+        stft_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "full":        # the configurations the benchmark numbers are quoted on
         which = sys.argv[2:] or ["infer64", "infer32", "grad64"]
         if "infer64" in which:   # BASELINE.json configs[1]: B=64, T_text=150, 800 steps, the bench weights (scale 1.0)
