@@ -312,6 +312,21 @@ int32_t t2_mel_spectrogram_frames(int32_t n_samples, int32_t hop_length);
 size_t  t2_mel_spectrogram_workspace_bytes(int32_t B, int32_t n_samples, int32_t filter_length, int32_t hop_length, int32_t n_mel);
 int     t2_mel_spectrogram(const T2MelSpecArgs* a, void* stream);
 
+/* ---- TextMelCollate on the device (data_utils.py:73-111): ragged batch in HBM -> the padded, length-sorted 5-tuple ------------
+ * text_flat: the B token sequences concatenated (int64), text_offsets (B + 1) their prefix offsets; mel_flat: the B
+ * (n_mel, L_i) row-major spectrograms concatenated, mel_offsets (B + 1) prefix offsets in FRAMES.  T_max >= longest text,
+ * L_pad >= longest mel (the caller rounds it up to a multiple of n_frames_per_step, data_utils.py:93-96).  Rows are ordered by
+ * decreasing text length (ties keep the original order); order[b] = source row of output row b.  All pointers device. */
+typedef struct T2CollateArgs {
+  const int64_t* text_flat; const int64_t* text_offsets;
+  const float* mel_flat; const int64_t* mel_offsets;
+  int32_t B, n_mel, T_max, L_pad;
+  int32_t* order;
+  int64_t* text_padded; int64_t* input_lengths;
+  float* mel_padded; float* gate_padded; int64_t* output_lengths;
+} T2CollateArgs;
+int t2_collate(const T2CollateArgs* a, void* stream);
+
 /* ---- Tacotron2.inference end to end with HOST buffers (model.py:517-529) ----------------------
  * text_host (B, T_text) int64 in (pinned) host memory -> mel_post_host (B, 80, T_cap) fp32,
  * mel_lengths_host (B), n_steps_host (1).  Copies H2D, runs encoder -> decoder -> postnet on

@@ -23,7 +23,7 @@ EXPORTS = [
     "t2_postnet_stash_bytes", "t2_postnet_backward_workspace_bytes", "t2_postnet_backward",
     "t2_clip_adam_workspace_bytes", "t2_clip_adam_step", "t2_amp_adam_workspace_bytes", "t2_amp_adam_step",
     "t2_loss_workspace_bytes", "t2_tacotron2_loss",
-    "t2_mel_spectrogram_frames", "t2_mel_spectrogram_workspace_bytes", "t2_mel_spectrogram",
+    "t2_mel_spectrogram_frames", "t2_mel_spectrogram_workspace_bytes", "t2_mel_spectrogram", "t2_collate",
 ]
 
 
@@ -115,6 +115,13 @@ class T2MelSpecArgs(C.Structure):
                 ("clip_val", C.c_float), ("mel", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class T2CollateArgs(C.Structure):
+    _fields_ = [("text_flat", C.c_void_p), ("text_offsets", C.c_void_p), ("mel_flat", C.c_void_p), ("mel_offsets", C.c_void_p),
+                ("B", C.c_int32), ("n_mel", C.c_int32), ("T_max", C.c_int32), ("L_pad", C.c_int32), ("order", C.c_void_p),
+                ("text_padded", C.c_void_p), ("input_lengths", C.c_void_p), ("mel_padded", C.c_void_p),
+                ("gate_padded", C.c_void_p), ("output_lengths", C.c_void_p)]
+
+
 class T2PostnetArgs(C.Structure):
     _fields_ = [("mel", C.c_void_p), ("mel_batch_stride", C.c_int64), ("lengths", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("training", C.c_int32), ("keep", C.c_void_p),
@@ -176,6 +183,7 @@ def lib():
     L.t2_mel_spectrogram_workspace_bytes.restype = C.c_size_t
     L.t2_mel_spectrogram_workspace_bytes.argtypes = [C.c_int32] * 5
     L.t2_mel_spectrogram.argtypes = [C.POINTER(T2MelSpecArgs), C.c_void_p]
+    L.t2_collate.argtypes = [C.POINTER(T2CollateArgs), C.c_void_p]
     L.t2_encoder_backward.argtypes = [C.c_void_p, C.POINTER(T2EncoderBwdArgs), C.c_void_p]
     L.t2_postnet_backward.argtypes = [C.c_void_p, C.POINTER(T2PostnetBwdArgs), C.c_void_p]
     L.t2_decoder_backward.argtypes = [C.c_void_p, C.POINTER(T2DecoderBwdArgs), C.c_void_p]

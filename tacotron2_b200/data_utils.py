@@ -39,3 +39,42 @@ class TextMelCollate:
         if self.pin_memory:
             out = tuple(t.pin_memory() for t in out)
         return out
+
+
+class DeviceTextMelCollate:
+    """``TextMelCollate`` for samples that already live on the GPU (e.g. mels straight out of ``TacotronSTFT.mel_spectrogram``):
+    one concatenation + ``t2_collate`` (rank by text length, pad, gate targets) instead of per-row host loops and five H2D
+    copies.  Same 5-tuple as the reference's collate function (data_utils.py:73-111), on the device, no host synchronisation:
+    the lengths come from the tensor shapes.  Rows with equal text length keep their input order."""
+
+    def __init__(self, n_frames_per_step):
+        self.n_frames_per_step = n_frames_per_step
+
+    def __call__(self, batch):
+        import ctypes as C
+        from . import _capi
+        L = _capi.lib()
+        dev = batch[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("DeviceTextMelCollate: the samples must be CUDA tensors (use TextMelCollate for host batches)")
+        B, n_mel = len(batch), int(batch[0][1].shape[0])
+        tlen, mlen = [int(x[0].numel()) for x in batch], [int(x[1].shape[1]) for x in batch]
+        text_flat = torch.cat([x[0].reshape(-1).to(device=dev, dtype=torch.int64) for x in batch])
+        mel_flat = torch.cat([x[1].to(dtype=torch.float32).contiguous().reshape(-1) for x in batch])
+        off = lambda v: torch.tensor([0] + list(torch.tensor(v).cumsum(0).tolist()), dtype=torch.int64).to(dev, non_blocking=True)
+        text_off, mel_off = off(tlen), off(mlen)
+        T_max, L_pad = max(tlen), max(mlen)
+        if L_pad % self.n_frames_per_step:
+            L_pad += self.n_frames_per_step - L_pad % self.n_frames_per_step
+        i64, f32 = dict(device=dev, dtype=torch.int64), dict(device=dev, dtype=torch.float32)
+        order = torch.empty(B, device=dev, dtype=torch.int32)
+        out = (torch.empty(B, T_max, **i64), torch.empty(B, **i64), torch.empty(B, n_mel, L_pad, **f32), torch.empty(B, L_pad, **f32),
+               torch.empty(B, **i64))
+        a = _capi.T2CollateArgs()
+        a.text_flat, a.text_offsets, a.mel_flat, a.mel_offsets = (t.data_ptr() for t in (text_flat, text_off, mel_flat, mel_off))
+        a.B, a.n_mel, a.T_max, a.L_pad, a.order = B, n_mel, T_max, L_pad, order.data_ptr()
+        a.text_padded, a.input_lengths, a.mel_padded, a.gate_padded, a.output_lengths = (t.data_ptr() for t in out)
+        with torch.cuda.device(dev):
+            _capi.check(L.t2_collate(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        self.order = order
+        return out

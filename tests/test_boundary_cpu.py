@@ -119,6 +119,15 @@ def test_ctypes_structs_match_c_layout(tmp_path):
                        "max_norm", "step", "grad_norm", "ws", "ws_bytes"],
         "T2PostnetArgs": ["mel", "mel_batch_stride", "lengths", "B", "T", "training", "keep", "seed",
                           "add_residual", "mel_post", "ws", "ws_bytes", "stash", "stash_bytes"],
+        "T2AmpAdamArgs": ["n", "model_params", "param_is_half", "grads", "grad_is_half", "master", "exp_avg", "exp_avg_sq", "numel",
+                          "lr", "beta1", "beta2", "eps", "weight_decay", "max_norm", "growth_interval", "growth_factor",
+                          "backoff_factor", "state", "grad_norm", "skipped", "ws", "ws_bytes"],
+        "T2LossArgs": ["mel", "mel_post", "gate", "mel_target", "gate_target", "output_lengths", "B", "C", "T", "loss", "d_mel",
+                       "d_mel_post", "d_gate", "ws", "ws_bytes"],
+        "T2MelSpecArgs": ["y", "B", "n_samples", "filter_length", "hop_length", "n_mel", "forward_basis", "mel_basis", "clip_val",
+                          "mel", "ws", "ws_bytes"],
+        "T2CollateArgs": ["text_flat", "text_offsets", "mel_flat", "mel_offsets", "B", "n_mel", "T_max", "L_pad", "order",
+                          "text_padded", "input_lengths", "mel_padded", "gate_padded", "output_lengths"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "t2b200.h"', 'int main(void){']
     for s, fs in fields.items():

@@ -311,3 +311,24 @@ def test_mel_spectrogram_vs_oracle(B, n, cfg):
     assert rel_err(torch.exp(got), torch.exp(ref)) < 1e-4                     # linear mel energies, relative to the maximum
     with pytest.raises(AssertionError):
         stft.mel_spectrogram((y * 3).cuda())                                  # layers.py:74-75 range check
+
+
+def test_device_collate_matches_host_collate():
+    """t2_collate (DeviceTextMelCollate) == the host TextMelCollate -- itself checked against the reference's collate function
+    in tests/test_boundary_cpu.py -- on ragged batches (distinct text lengths: ties are ordered by input position on the
+    device, by torch.sort on the host)."""
+    from tacotron2_b200.data_utils import DeviceTextMelCollate, TextMelCollate
+    g = torch.Generator().manual_seed(5)
+    for B, nfs in [(1, 1), (7, 1), (64, 2)]:
+        tls = torch.randperm(200, generator=g)[:B] + 1
+        batch = [(torch.randint(1, 148, (int(tls[i]),), generator=g), torch.randn(80, int(torch.randint(1, 300, (1,), generator=g)), generator=g))
+                 for i in range(B)]
+        ref = TextMelCollate(nfs)(batch)
+        got = DeviceTextMelCollate(nfs)([(t.cuda(), m.cuda()) for t, m in batch])
+        torch.cuda.synchronize()
+        for a, b in zip(got, ref):
+            assert a.dtype == b.dtype and torch.equal(a.cpu(), b)
+    # ties: stable by input position
+    batch = [(torch.full((5,), i + 1), torch.randn(80, 3 + i, generator=g)) for i in range(4)]
+    got = DeviceTextMelCollate(1)([(t.cuda(), m.cuda()) for t, m in batch])
+    assert got[0][:, 0].cpu().tolist() == [1, 2, 3, 4] and got[4].cpu().tolist() == [3, 4, 5, 6]
