@@ -280,7 +280,9 @@ def train_block(t2, hp, rank, world, iters=3, warmup=2):
         if world > 1:
             dist.barrier()
         rows = [one_step() for _ in range(iters)]
-        t = torch.tensor([sum(r[0][k] for r in rows) / iters for k in range(3)], device="cuda", dtype=torch.float64)
+        rows.sort(key=lambda r: sum(r[0]))
+        med = rows[len(rows) // 2]                                                 # the median step (by total time)
+        t = torch.tensor(med[0], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t.cpu()], rows[-1][1]
@@ -308,7 +310,7 @@ def train_block(t2, hp, rank, world, iters=3, warmup=2):
     return out
 
 
-def config5_block(t2, hp, rank, world, iters=2):
+def config5_block(t2, hp, rank, world, iters=3):
     """BASELINE.json configs[4]: long-sequence inference B=256 over 8 GPUs = 32 rows per GPU, T_text=300, 2000 decoder
     steps (gate_threshold = 1.0); per-GPU share measured on every rank, max over ranks."""
     import contextlib
@@ -330,7 +332,8 @@ def config5_block(t2, hp, rank, world, iters=2):
         if it:
             ms.append(e0.elapsed_time(e1))
     assert out[0].shape == (32, 80, 2000)
-    t = torch.tensor([sum(ms) / len(ms)], device="cuda", dtype=torch.float64)
+    ms.sort()
+    t = torch.tensor([ms[len(ms) // 2]], device="cuda", dtype=torch.float64)      # median of the timed iterations
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     m = float(t.cpu())
