@@ -109,8 +109,11 @@ class _EngineOwner(object):
             named[prefix + k] = v
         # under autograd in training mode the parameters change every step (possibly through .data, which the version
         # counter does not see): always re-pack there; otherwise the (pointer, version, dtype) key decides
-        eng.ensure(named, force=root.training and torch.is_grad_enabled() and
-                   any(p_.requires_grad for p_ in root.parameters()))
+        # ... once per top-level call: the modules Tacotron2.forward calls in turn (embedding + encoder, decoder, postnet)
+        # share the packing done at its start (root._t2_packed_in_call), they do not repeat it
+        force = (root.training and torch.is_grad_enabled() and not root.__dict__.get("_t2_packed_in_call", False) and
+                 any(p_.requires_grad for p_ in root.parameters()))
+        eng.ensure(named, force=force)
         return eng
 
     def _t2_out_dtype(self):
@@ -163,6 +166,8 @@ class _EncoderFn(torch.autograd.Function):
         if embedded is not None:
             emb32 = embedded.detach().to(dtype=torch.float32).contiguous()
         memory = eng.encoder(text=text, embedded=emb32, lengths=lengths, training=training, keep=keep, stash=stash, seed=seed)
+        if training and not owner._t2_root().__dict__.get("_t2_packed_in_call", False):
+            eng.invalidate()              # running statistics changed under the packed copies (see Tacotron2._forward_packed)
         ctx.saved = dict(eng=eng, text=text, embedded=emb32, lengths=lengths, training=training, keep=keep, seed=seed,
                          stash=stash, names=prefix_params, params=params,
                          emb_dtype=embedded.dtype if embedded is not None else None)
@@ -196,6 +201,8 @@ class _PostnetFn(torch.autograd.Function):
         B, T = int(x.shape[0]), int(x.shape[1])
         stash = eng.stash_buffer("postnet", B, T)
         out = eng.postnet(x, None, add_residual, training, keep, stash=stash, seed=seed)
+        if training and not owner._t2_root().__dict__.get("_t2_packed_in_call", False):
+            eng.invalidate()
         ctx.saved = dict(eng=eng, B=B, T=T, add_residual=add_residual, training=training, keep=keep, seed=seed, stash=stash,
                          names=names, params=params, in_dtype=mel_btc.dtype, wgrad_lengths=wgrad_lengths)
         return out
@@ -509,7 +516,14 @@ class Tacotron2(_EngineOwner, nn.Module):
         """model.py:499-515."""
         text_inputs, text_lengths, mels, max_len, output_lengths = inputs
         text_lengths, output_lengths = text_lengths.data, output_lengths.data
-        eng = self._t2_engine()
+        eng = self._t2_engine()                       # (re-)packs the weights once for the whole forward pass
+        self.__dict__["_t2_packed_in_call"] = True
+        try:
+            return self._forward_packed(eng, text_inputs, text_lengths, mels, output_lengths)
+        finally:
+            self.__dict__["_t2_packed_in_call"] = False
+
+    def _forward_packed(self, eng, text_inputs, text_lengths, mels, output_lengths):
         masks = current_masks()
         grad = _wants_grad(self)
         if grad:
@@ -538,6 +552,9 @@ class Tacotron2(_EngineOwner, nn.Module):
             for mod in self.modules():
                 if isinstance(mod, nn.BatchNorm1d) and mod.num_batches_tracked is not None:
                     mod.num_batches_tracked += 1
+            # the kernels updated the BatchNorm running statistics through raw pointers (no torch version bump); the
+            # BN-folded inference images must not outlive them: next call re-packs
+            eng.invalidate()
         outputs = [mel_outputs, mel_outputs_postnet, gate_outputs, alignments]
         cast = self.__dict__.get("_t2_cast_outputs")     # amp.initialize(opt_level="O2"): outputs in fp32 for the loss
         if cast is not None:

@@ -406,3 +406,35 @@ def test_fused_loss_and_gradient_seeds_vs_oracle(B, T):
     torch.cuda.synchronize()
     assert abs(float(out[0]) - float(ref_m)) < 2e-6 * abs(float(ref_m))
     assert torch.equal(m_d.cpu(), mel.masked_fill(pad[:, None, :], 0.0)) and torch.equal(g_d.cpu(), gate.masked_fill(pad, 1e3))
+
+
+def test_running_statistics_updated_by_a_training_forward_reach_the_next_inference():
+    """The training-mode kernels update the BatchNorm running statistics through raw pointers (torch's version counters do not
+    move); the BN-folded inference images must be rebuilt before the next eval-mode call even when no optimizer step happened in
+    between."""
+    sd = synth_state_dict(seed=3, gate_bias=-10.0, scale=2.0)
+    model = t2.Tacotron2(t2.create_hparams())
+    model.load_state_dict(sd)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(0)
+    text = torch.randint(0, 148, (3, 17), generator=g).cuda()
+    keep = keep_mask((6, 2, 3, 256), 0.5, 1)
+    model.decoder.max_decoder_steps = 6
+    model.eval()
+    with torch.no_grad(), t2.dropout_masks(prenet=keep):
+        before = model.inference(text)[1].clone()
+    model.train()
+    tl = torch.tensor([17, 12, 9]).cuda(); ol = torch.tensor([5, 4, 3]).cuda()
+    mels = torch.randn(3, 80, 5, generator=g).cuda()
+    with torch.no_grad():
+        model((text, tl, mels, 17, ol))                       # updates running_mean / running_var (momentum 0.1), nothing else
+    model.eval()
+    with torch.no_grad(), t2.dropout_masks(prenet=keep):
+        after = model.inference(text)[1].clone()
+    fresh = t2.Tacotron2(t2.create_hparams())
+    fresh.load_state_dict(model.state_dict())
+    fresh = fresh.cuda().eval()
+    fresh.decoder.max_decoder_steps = 6
+    with torch.no_grad(), t2.dropout_masks(prenet=keep):
+        want = fresh.inference(text)[1]
+    assert rel_err(after, want) < 1e-6 and rel_err(before, want) > 1e-4
