@@ -281,12 +281,14 @@ struct ConvLayer {
   const uint8_t* wimg_fwd;           // tensor-core weight image of the forward conv (conv_tc.cu), packed by pack_model
   uint8_t** wimg_dgrad;              // storage of the flipped / transposed image of the input-gradient conv
 };
-// tensor-core conv path of the training forward / input gradient: planes scratch (null = plain cuBLAS GEMMs)
+// tensor-core conv path of the training forward / input gradient: planes scratch (null = row-shifted GEMMs through gemm_rm)
 struct TcTrain { __half* planes; };
-// T2_CONV_TRAIN: which training-mode convolutions run on the tensor-core engine (conv_tc.cu) instead of plain cuBLAS fp32
-// GEMMs.  Default "dgrad": the input gradients only -- the forward through it measured 2e-2 gradient error on one
-// ill-conditioned test shape (near-constant BatchNorm channels amplify its ~1e-5 output error), so the training forward
-// stays fp32 until that is understood; "both" / "fwd" / "cublas" select the other combinations.
+// T2_CONV_TRAIN: which training-mode convolutions run on the implicit-GEMM conv engine (conv_tc.cu) instead of 5 row-shifted
+// products on the general tensor-core GEMM (gemm_tc.cu through gemm_rm; cuBLAS only with T2_GEMM=cublas).  Default "dgrad": the
+// input gradients only -- the conv engine accumulates ~100-480 MMAs in one TMEM chain (3e-6 ... 1e-5 output error; the
+// accumulator update truncates) and near-constant BatchNorm channels amplify that to a 2e-2 gradient error on one
+// ill-conditioned test shape, so the training FORWARD uses gemm_tc (one chain per 64-wide K chunk, 7e-7);
+// "both" / "fwd" / "cublas" (= "gemm": neither on conv_tc) select the other combinations.
 int tc_train_mode() {
   const char* e = getenv("T2_CONV_TRAIN");
   if (!e) return 2;

@@ -1,4 +1,5 @@
-"""Probe: training-mode Encoder / Postnet forward outputs, tensor-core conv forward vs cuBLAS fp32, vs the oracle."""
+"""Probe: training-mode Encoder / Postnet forward outputs vs the oracle: convs as row-shifted products on gemm_tc
+(T2_CONV_TRAIN=cublas, the historical name of "not on conv_tc"; add T2_GEMM=cublas for real cuBLAS) vs the conv_tc engine (fwd)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
