@@ -257,3 +257,27 @@ def test_engine_cache_key_and_invalidation():
     eng.key = ("something",)
     model.decoder.invalidate_weights()                            # through a child
     assert eng.key is None
+
+
+def test_bench_roofline_traffic_is_keyed_to_the_kernel_source(tmp_path, monkeypatch):
+    """bench.py takes roofline.traffic from profiles/decoder_traffic.json only while decoder_persistent.cu still hashes to the
+    captured source; anything else gives None (never a stale literal)."""
+    import hashlib
+    import json
+    import bench
+    src = open(os.path.join(ROOT, "tacotron2_b200", "csrc", "decoder_persistent.cu"), "rb").read()
+    rec = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json")))
+    val, why = bench.decoder_traffic()
+    if rec["source_sha16"] == hashlib.sha256(src).hexdigest()[:16]:
+        assert val == rec["dram_bytes_per_step"] and val > 1e6
+    else:
+        assert val is None and "stale" in why
+    # a modified source invalidates the record
+    fake = tmp_path / "repo"
+    (fake / "profiles").mkdir(parents=True)
+    (fake / "tacotron2_b200" / "csrc").mkdir(parents=True)
+    (fake / "profiles" / "decoder_traffic.json").write_text(json.dumps(rec))
+    (fake / "tacotron2_b200" / "csrc" / "decoder_persistent.cu").write_bytes(src + b"\n// edited\n")
+    monkeypatch.setattr(bench, "ROOT", str(fake))
+    val, why = bench.decoder_traffic()
+    assert val is None and "stale" in why
